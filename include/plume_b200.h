@@ -1,0 +1,151 @@
+/*
+ * plume_b200.h -- C ABI of the B200-native batch PLUME signer / verifier.
+ *
+ * This is the drop-in boundary for the per-signature hot path of the reference crate
+ * `plume_rustcrypto` (plume-sig/zk-nullifier-sig, rust-k256/).  The reference has no FFI of its
+ * own; each entry point below states which reference function it replaces, so that a Rust shim
+ *  can keep `PlumeSignature::sign_v1 / sign_v2 / verify` and forward batches here.
+ *
+ * Conventions
+ *   - scalars and field elements: 32 bytes, big-endian (k256 `FieldBytes` / SEC1 order);
+ *   - curve points: 64 bytes `x || y` (affine, big-endian); 64 zero bytes denote the identity;
+ *   - all arrays are structure-of-arrays, item i at offset i * element_size;
+ *   - messages: either `msg_offsets` (n + 1 byte offsets into `msgs`) or, when it is NULL,
+ *     fixed-length records of `msg_len` bytes each;
+ *   - functions return 0 on success and a negative PLUME_E_* code on failure
+ *     (text via plume_last_error); nothing ever aborts or unwinds across this boundary;
+ *   - per-item failures are reported in `status[i]` (sign) / `ok[i]` (verify);
+ *   - a context is externally synchronised: one batch call at a time per context.
+ *   - `_device` variants take device pointers (16-byte aligned for the 32/64-byte arrays) and
+ *     enqueue on the caller's CUDA stream without synchronising; the plain variants take host
+ *     pointers, stage them through pinned buffers and return when the results are in place.
+ *
+ * There is no CPU fallback: every entry point fails with PLUME_E_NO_DEVICE / PLUME_E_CUDA when
+ * the CUDA device or kernels are unavailable.
+ */
+#ifndef PLUME_B200_H
+#define PLUME_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLUME_ABI_VERSION 1
+
+/* return codes */
+#define PLUME_OK 0
+#define PLUME_E_ARG (-1)        /* bad argument (null pointer, version not 1/2, ...) */
+#define PLUME_E_NO_DEVICE (-2)  /* no CUDA device / device index out of range */
+#define PLUME_E_CUDA (-3)       /* CUDA runtime error, see plume_last_error */
+#define PLUME_E_NOMEM (-4)      /* allocation failed */
+
+/* per-item status of plume_sign_batch: the places where the reference panics
+ * (rust-k256/src/randomizedsigner.rs:61, :91, :95) or rejects its inputs */
+#define PLUME_STATUS_OK 0
+#define PLUME_STATUS_BAD_R 1    /* r not in [1, n-1]   (SecretKey::random never yields it; :49) */
+#define PLUME_STATUS_BAD_SK 2   /* sk not in [1, n-1]  (SecretKey::from_bytes rejects it) */
+#define PLUME_STATUS_BAD_C 3    /* SHA-256 output c = 0 or c >= n (NonZeroScalar::from_repr, :90-91) */
+#define PLUME_STATUS_ZERO_S 4   /* s = r + c*sk = 0 (:95) */
+#define PLUME_STATUS_H_INF 5    /* hash_to_curve returned the identity (:61) */
+
+typedef struct plume_ctx plume_ctx;
+
+/* ABI / library identification. */
+int plume_version(void);
+
+/* Create a context on CUDA device `device` (ordinal as seen by the CUDA runtime in this
+ * process).  Builds the fixed-base table for the generator on the device (one-off, a few ms).
+ * `fixed_window_bits` = 0 picks the default; otherwise 4..16.
+ * A multi-GPU job is one process (context) per GPU, each given its contiguous range of the
+ * batch; nothing is shared between contexts. */
+int plume_ctx_create(plume_ctx** out, int device, int fixed_window_bits);
+void plume_ctx_destroy(plume_ctx* ctx);
+
+/* Last error text of this context (or of context creation when ctx is NULL). */
+const char* plume_last_error(const plume_ctx* ctx);
+
+/* Largest batch one call processes in a single pass; bigger batches are cut into chunks. */
+size_t plume_ctx_chunk_items(const plume_ctx* ctx);
+
+/*
+ * Batch signing.  Replaces PlumeSigner::try_sign_with_rng (rust-k256/src/randomizedsigner.rs:43-112)
+ * behind PlumeSignature::sign_v1 / sign_v2 (rust-k256/src/lib.rs:149-156).  The nonce r that the
+ * reference draws with SecretKey::random(rng) (:49) is an input: the RNG stays on the caller's
+ * side of the boundary.
+ *   version            1 or 2
+ *   sk, r              n x 32
+ *   pk, nullifier      n x 64   out: g^sk, hash_to_curve(m, pk)^sk
+ *   c, s               n x 32   out
+ *   r_point            n x 64   out: g^r           (V1 field; may be NULL)
+ *   hashed_to_curve_r  n x 64   out: h^r           (V1 field; may be NULL)
+ *   status             n        out: PLUME_STATUS_*; on a non-zero status every output of the item is zero
+ */
+int plume_sign_batch(plume_ctx* ctx, int version, size_t n,
+                     const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                     const uint8_t* sk, const uint8_t* r,
+                     uint8_t* pk, uint8_t* nullifier, uint8_t* c, uint8_t* s,
+                     uint8_t* r_point, uint8_t* hashed_to_curve_r, uint8_t* status);
+
+/*
+ * Batch verification.  Replaces PlumeSignature::verify (rust-k256/src/lib.rs:93-145).
+ *   version 1: r_point and hashed_to_curve_r are required (v1specific = Some{..});
+ *   version 2: they are ignored (v1specific = None).
+ *   ok[i] = 1 iff the reference's verify() returns true.  Inputs that the reference's types
+ *   cannot represent (off-curve or non-canonical points, c or s outside [1, n-1]) give 0.
+ */
+int plume_verify_batch(plume_ctx* ctx, int version, size_t n,
+                       const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                       const uint8_t* pk, const uint8_t* nullifier, const uint8_t* c, const uint8_t* s,
+                       const uint8_t* r_point, const uint8_t* hashed_to_curve_r, uint8_t* ok);
+
+/*
+ * Batch hash-to-curve on caller-assembled preimages: out[i] = hash_to_curve(msgs[i]) with the
+ * PLUME DST.  Replaces utils::hash_to_curve (rust-k256/src/utils.rs:11-20), whose preimage is
+ * m || SEC1-compressed(pk); the caller concatenates.
+ *   out  n x 64
+ */
+int plume_hash_to_curve_batch(plume_ctx* ctx, size_t n,
+                              const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                              uint8_t* out);
+
+/* Device-pointer variants: all pointers are device memory of the context's GPU, `stream` is a
+ * cudaStream_t (passed as void* to keep CUDA headers out of this file).  n must not exceed
+ * plume_ctx_chunk_items().  Work is enqueued; the caller synchronises the stream. */
+int plume_sign_batch_device(plume_ctx* ctx, int version, size_t n,
+                            const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                            const uint8_t* sk, const uint8_t* r,
+                            uint8_t* pk, uint8_t* nullifier, uint8_t* c, uint8_t* s,
+                            uint8_t* r_point, uint8_t* hashed_to_curve_r, uint8_t* status, void* stream);
+int plume_verify_batch_device(plume_ctx* ctx, int version, size_t n,
+                              const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                              const uint8_t* pk, const uint8_t* nullifier, const uint8_t* c, const uint8_t* s,
+                              const uint8_t* r_point, const uint8_t* hashed_to_curve_r, uint8_t* ok, void* stream);
+int plume_hash_to_curve_batch_device(plume_ctx* ctx, size_t n,
+                                     const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                                     uint8_t* out, void* stream);
+
+/* Number of kernel launches this context has enqueued so far (bench.py's `gpu_launches`). */
+uint64_t plume_ctx_launch_count(const plume_ctx* ctx);
+
+/* Per-stage device timing, measured with CUDA events on the launching stream.  After
+ * plume_ctx_set_profiling(ctx, 1) every stage launch is bracketed by an event pair;
+ * plume_ctx_stage_ms returns the summed duration in milliseconds of all launches of the named
+ * stage since profiling was switched on (and their number in *launches), synchronising the
+ * context's streams first.  Stage names: "sign_fixed", "sign_h2c", "sign_varbase", "sign_final",
+ * "verify_h2c", "verify_muls", "verify_final", "h2c_map", "h2c_out", "binv".
+ * Returns a negative value for an unknown stage.  set_profiling(ctx, 1) also resets the sums. */
+int plume_ctx_set_profiling(plume_ctx* ctx, int on);
+double plume_ctx_stage_ms(plume_ctx* ctx, const char* stage, uint64_t* launches);
+
+/* Integer-pipe microbenchmark: runs `iters` rounds of independent IMAD.WIDE.U32 chains on every SM
+ * and returns the measured 32x32->64 multiply-add rate (limb products per second), the
+ * denominator of the integer-ALU roofline (SURVEY.md section 8d "Peak"). */
+int plume_measure_imad_peak(plume_ctx* ctx, int iters, double* limb_products_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLUME_B200_H */

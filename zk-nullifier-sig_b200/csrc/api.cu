@@ -1,0 +1,530 @@
+// api.cu -- the C ABI of include/plume_b200.h: context, chunked double-buffered execution of the
+// stage pipelines, host staging, per-stage event timing.  No CPU fallback lives here: without a
+// CUDA device every entry point fails.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/plume_b200.h"
+#include "launch.h"
+
+namespace {
+
+const char* const kStageNames[] = {"sign_fixed", "sign_h2c", "sign_varbase", "sign_final", "verify_h2c",
+                                   "verify_muls", "verify_final", "h2c_map", "h2c_out", "binv"};
+enum Stage { ST_SIGN_FIXED, ST_SIGN_H2C, ST_SIGN_VARBASE, ST_SIGN_FINAL, ST_VERIFY_H2C, ST_VERIFY_MULS,
+             ST_VERIFY_FINAL, ST_H2C_MAP, ST_H2C_OUT, ST_BINV, ST_COUNT };
+
+struct PendingCopy { void* dst; const void* src; size_t bytes; };
+
+struct Lane {
+    cudaStream_t stream = nullptr;
+    uint32_t* ws = nullptr;          // WS_SLOTS * chunk * 32 bytes
+    uint8_t* d_io = nullptr;         // device arena for inputs and outputs of one chunk
+    size_t d_io_cap = 0, d_io_used = 0;
+    uint8_t* h_stage = nullptr;      // pinned staging arena (same layout as d_io)
+    size_t h_cap = 0;
+    std::vector<PendingCopy> pending;  // staged outputs to hand to the caller after the stream drains
+    bool busy = false;
+};
+
+std::string g_create_error;
+
+}  // namespace
+
+struct plume_ctx {
+    int device = 0;
+    int gw = 0;
+    uint32_t* gtab = nullptr;
+    size_t chunk = 0;
+    uint32_t binv_k = 16;
+    Lane lanes[2];
+    std::string err;
+    uint64_t launches = 0;
+    bool profiling = false;
+    struct Ev { int stage; cudaEvent_t a, b; };
+    std::vector<Ev> events;
+    double stage_ms[ST_COUNT] = {0};
+    uint64_t stage_n[ST_COUNT] = {0};
+};
+
+namespace {
+
+int fail(plume_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(ctx, PLUME_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));   \
+    } while (0)
+
+size_t env_size(const char* name, size_t dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    long long x = atoll(v);
+    return x > 0 ? (size_t)x : dflt;
+}
+
+struct ScopedDevice {
+    int prev = -1;
+    explicit ScopedDevice(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~ScopedDevice() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// one stage launch, counted and (optionally) bracketed by an event pair on the launching stream
+template <class F>
+int run_stage(plume_ctx* ctx, int stage, cudaStream_t s, F&& launch) {
+    cudaEvent_t a = nullptr, b = nullptr;
+    if (ctx->profiling) {
+        CU(cudaEventCreate(&a));
+        CU(cudaEventCreate(&b));
+        CU(cudaEventRecord(a, s));
+    }
+    CU(launch());
+    ctx->launches++;
+    if (ctx->profiling) {
+        CU(cudaEventRecord(b, s));
+        ctx->events.push_back({stage, a, b});
+    }
+    return PLUME_OK;
+}
+#define RUN(stage, expr)                                                             \
+    do {                                                                             \
+        int rc__ = run_stage(ctx, stage, s, [&]() -> cudaError_t { return (expr); }); \
+        if (rc__ != PLUME_OK) return rc__;                                           \
+    } while (0)
+
+int binv(plume_ctx* ctx, uint32_t* ws, uint32_t n, uint32_t m, cudaStream_t s) {
+    RUN(ST_BINV, launch_binv(ws + (size_t)WS_Z0 * n * 8, ws + (size_t)WS_P0 * n * 8, m, ctx->binv_k, s));
+    return PLUME_OK;
+}
+
+int enqueue_sign(plume_ctx* ctx, sign_args a, cudaStream_t s) {
+    RUN(ST_SIGN_FIXED, launch_sign_fixed(a, s));
+    if (int rc = binv(ctx, a.ws, a.n, 2 * a.n, s)) return rc;
+    RUN(ST_SIGN_H2C, launch_sign_h2c(a, s));
+    if (int rc = binv(ctx, a.ws, a.n, a.n, s)) return rc;
+    RUN(ST_SIGN_VARBASE, launch_sign_varbase(a, s));
+    if (int rc = binv(ctx, a.ws, a.n, 2 * a.n, s)) return rc;
+    RUN(ST_SIGN_FINAL, launch_sign_final(a, s));
+    return PLUME_OK;
+}
+int enqueue_verify(plume_ctx* ctx, verify_args a, cudaStream_t s) {
+    RUN(ST_VERIFY_H2C, launch_verify_h2c(a, s));
+    if (int rc = binv(ctx, a.ws, a.n, a.n, s)) return rc;
+    RUN(ST_VERIFY_MULS, launch_verify_muls(a, s));
+    if (int rc = binv(ctx, a.ws, a.n, 2 * a.n, s)) return rc;
+    RUN(ST_VERIFY_FINAL, launch_verify_final(a, s));
+    return PLUME_OK;
+}
+int enqueue_h2c(plume_ctx* ctx, h2c_args a, cudaStream_t s) {
+    RUN(ST_H2C_MAP, launch_h2c_map(a, s));
+    if (int rc = binv(ctx, a.ws, a.n, a.n, s)) return rc;
+    RUN(ST_H2C_OUT, launch_h2c_out(a, s));
+    return PLUME_OK;
+}
+
+bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// ---- lane arenas ---------------------------------------------------------------------------------------
+int lane_reserve(plume_ctx* ctx, Lane& L, size_t bytes) {
+    if (bytes <= L.d_io_cap) return PLUME_OK;
+    size_t cap = bytes + bytes / 4;
+    if (L.d_io) { cudaFree(L.d_io); L.d_io = nullptr; }
+    if (L.h_stage) { cudaFreeHost(L.h_stage); L.h_stage = nullptr; }
+    L.d_io_cap = L.h_cap = 0;
+    CU(cudaMalloc(&L.d_io, cap));
+    CU(cudaHostAlloc(&L.h_stage, cap, cudaHostAllocDefault));
+    L.d_io_cap = L.h_cap = cap;
+    return PLUME_OK;
+}
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+// carve `bytes` out of the lane arena; returns the offset
+size_t lane_take(Lane& L, size_t bytes) {
+    size_t off = L.d_io_used;
+    L.d_io_used = align256(off + bytes);
+    return off;
+}
+// device copy of a host input array
+int lane_input(plume_ctx* ctx, Lane& L, const void* host, size_t bytes, uint8_t** dev) {
+    size_t off = lane_take(L, bytes);
+    *dev = L.d_io + off;
+    if (bytes == 0) return PLUME_OK;
+    const void* src = host;
+    if (!is_pinned(host)) {
+        memcpy(L.h_stage + off, host, bytes);
+        src = L.h_stage + off;
+    }
+    CU(cudaMemcpyAsync(*dev, src, bytes, cudaMemcpyHostToDevice, L.stream));
+    return PLUME_OK;
+}
+uint8_t* lane_output(Lane& L, size_t bytes, size_t* off_out) {
+    size_t off = lane_take(L, bytes);
+    *off_out = off;
+    return L.d_io + off;
+}
+int lane_fetch(plume_ctx* ctx, Lane& L, void* host, size_t off, size_t bytes) {
+    if (bytes == 0 || host == nullptr) return PLUME_OK;
+    if (is_pinned(host)) {
+        CU(cudaMemcpyAsync(host, L.d_io + off, bytes, cudaMemcpyDeviceToHost, L.stream));
+    } else {
+        CU(cudaMemcpyAsync(L.h_stage + off, L.d_io + off, bytes, cudaMemcpyDeviceToHost, L.stream));
+        L.pending.push_back({host, L.h_stage + off, bytes});
+    }
+    return PLUME_OK;
+}
+int lane_finish(plume_ctx* ctx, Lane& L) {
+    if (!L.busy) return PLUME_OK;
+    CU(cudaStreamSynchronize(L.stream));
+    for (const PendingCopy& p : L.pending) memcpy(p.dst, p.src, p.bytes);
+    L.pending.clear();
+    L.busy = false;
+    return PLUME_OK;
+}
+
+struct MsgChunk { const uint8_t* base; size_t bytes; const uint64_t* offs; uint64_t first; };
+
+// stage the messages of items [i0, i0+cn): returns device views
+int lane_msgs(plume_ctx* ctx, Lane& L, const uint8_t* msgs, const uint64_t* offs, size_t msg_len, size_t i0, size_t cn,
+              msg_view* view) {
+    uint8_t* d_msgs = nullptr;
+    if (offs) {
+        uint64_t b0 = offs[i0], b1 = offs[i0 + cn];
+        if (int rc = lane_input(ctx, L, msgs + b0, (size_t)(b1 - b0), &d_msgs)) return rc;
+        // rebased offsets
+        size_t off = lane_take(L, (cn + 1) * sizeof(uint64_t));
+        uint64_t* h = reinterpret_cast<uint64_t*>(L.h_stage + off);
+        for (size_t i = 0; i <= cn; i++) h[i] = offs[i0 + i] - b0;
+        CU(cudaMemcpyAsync(L.d_io + off, h, (cn + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, L.stream));
+        view->base = d_msgs;
+        view->offs = reinterpret_cast<const uint64_t*>(L.d_io + off);
+        view->fixed_len = 0;
+    } else {
+        if (int rc = lane_input(ctx, L, msgs + i0 * msg_len, cn * msg_len, &d_msgs)) return rc;
+        view->base = d_msgs;
+        view->offs = nullptr;
+        view->fixed_len = (uint32_t)msg_len;
+    }
+    return PLUME_OK;
+}
+size_t msgs_bytes(const uint64_t* offs, size_t msg_len, size_t i0, size_t cn) {
+    return offs ? (size_t)(offs[i0 + cn] - offs[i0]) + (cn + 1) * 8 + 512 : cn * msg_len + 256;
+}
+
+int check_common(plume_ctx* ctx, size_t n, const uint8_t* msgs, const uint64_t* offs, size_t msg_len) {
+    if (!ctx) return PLUME_E_ARG;
+    if (n > 0 && !msgs && (offs ? offs[n] != offs[0] : msg_len != 0)) return fail(ctx, PLUME_E_ARG, "msgs is null");
+    if (!offs && msg_len > 0xFFFFFFFFull) return fail(ctx, PLUME_E_ARG, "msg_len too large");
+    return PLUME_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int plume_version(void) { return PLUME_ABI_VERSION; }
+
+const char* plume_last_error(const plume_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+size_t plume_ctx_chunk_items(const plume_ctx* ctx) { return ctx ? ctx->chunk : 0; }
+uint64_t plume_ctx_launch_count(const plume_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void plume_ctx_destroy(plume_ctx* ctx) {
+    if (!ctx) return;
+    ScopedDevice sd(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& e : ctx->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (Lane& L : ctx->lanes) {
+        if (L.ws) cudaFree(L.ws);
+        if (L.d_io) cudaFree(L.d_io);
+        if (L.h_stage) cudaFreeHost(L.h_stage);
+        if (L.stream) cudaStreamDestroy(L.stream);
+    }
+    if (ctx->gtab) cudaFree(ctx->gtab);
+    delete ctx;
+}
+
+int plume_ctx_create(plume_ctx** out, int device, int fixed_window_bits) {
+    plume_ctx* ctx = nullptr;  // CU() reports into g_create_error while ctx is null
+    if (!out) return fail(nullptr, PLUME_E_ARG, "out is null");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, PLUME_E_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, PLUME_E_NO_DEVICE, "device ordinal out of range");
+    int w = fixed_window_bits ? fixed_window_bits : (int)env_size("PLUME_FIXED_WINDOW", 12);
+    if (w < 4 || w > 16) return fail(nullptr, PLUME_E_ARG, "fixed_window_bits must be in 4..16");
+    ScopedDevice sd(device);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(nullptr, PLUME_E_NO_DEVICE, std::string("device is not sm_100 class: ") + prop.name);
+    CU(kernels_init());
+    plume_ctx* c = new plume_ctx();
+    c->device = device;
+    c->gw = w;
+    c->chunk = env_size("PLUME_CHUNK_ITEMS", (size_t)1 << 18);
+    c->binv_k = (uint32_t)env_size("PLUME_BINV_K", 16);
+    struct Guard { plume_ctx* c; ~Guard() { if (c) plume_ctx_destroy(c); } } guard{c};
+    for (Lane& L : c->lanes) {
+        CU(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+        CU(cudaMalloc(&L.ws, (size_t)WS_SLOTS * c->chunk * 32));
+    }
+    // generator table: entries -> batched inversion -> affine
+    const int nwin = (256 + w - 1) / w;
+    const size_t ne = (size_t)nwin << w;
+    uint32_t *bases = nullptr, *zs = nullptr, *scratch = nullptr;
+    CU(cudaMalloc(&c->gtab, ne * 64));
+    CU(cudaMalloc(&bases, (size_t)nwin * 64));
+    CU(cudaMalloc(&zs, ne * 32));
+    CU(cudaMalloc(&scratch, ne * 32));
+    cudaStream_t s = c->lanes[0].stream;
+    CU(launch_gtab_bases(bases, w, s));
+    CU(launch_gtab_entries((uint32_t)ne, c->gtab, zs, bases, w, s));
+    CU(launch_binv(zs, scratch, (uint32_t)ne, 16, s));
+    CU(launch_gtab_norm((uint32_t)ne, c->gtab, zs, s));
+    CU(cudaStreamSynchronize(s));
+    cudaFree(bases); cudaFree(zs); cudaFree(scratch);
+    guard.c = nullptr;
+    *out = c;
+    return PLUME_OK;
+}
+
+int plume_ctx_set_profiling(plume_ctx* ctx, int on) {
+    if (!ctx) return PLUME_E_ARG;
+    ScopedDevice sd(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& e : ctx->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    ctx->events.clear();
+    for (int i = 0; i < ST_COUNT; i++) { ctx->stage_ms[i] = 0; ctx->stage_n[i] = 0; }
+    ctx->profiling = on != 0;
+    return PLUME_OK;
+}
+
+double plume_ctx_stage_ms(plume_ctx* ctx, const char* stage, uint64_t* launches) {
+    if (!ctx || !stage) return -1.0;
+    int id = -1;
+    for (int i = 0; i < ST_COUNT; i++) if (strcmp(stage, kStageNames[i]) == 0) id = i;
+    if (id < 0) return -1.0;
+    ScopedDevice sd(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& e : ctx->events) {  // fold finished event pairs into the sums
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) { ctx->stage_ms[e.stage] += ms; ctx->stage_n[e.stage]++; }
+        cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    }
+    ctx->events.clear();
+    if (launches) *launches = ctx->stage_n[id];
+    return ctx->stage_ms[id];
+}
+
+int plume_measure_imad_peak(plume_ctx* ctx, int iters, double* lp_per_s) {
+    if (!ctx || !lp_per_s || iters <= 0) return PLUME_E_ARG;
+    ScopedDevice sd(ctx->device);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, ctx->device));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8;
+    uint32_t* sink = nullptr;
+    CU(cudaMalloc(&sink, 64));
+    cudaStream_t s = ctx->lanes[0].stream;
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    CU(launch_imad_peak(sink, iters, blocks, threads, s));  // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        CU(cudaEventRecord(a, s));
+        CU(launch_imad_peak(sink, iters, blocks, threads, s));
+        CU(cudaEventRecord(b, s));
+        CU(cudaEventSynchronize(b));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, a, b));
+        double rate = (double)blocks * threads * (double)iters * 64.0 / (ms * 1e-3);
+        if (rate > best) best = rate;
+    }
+    ctx->launches += 6;
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(sink);
+    *lp_per_s = best;
+    return PLUME_OK;
+}
+
+// ---- device-pointer variants ---------------------------------------------------------------------------------
+int plume_sign_batch_device(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets,
+                            size_t msg_len, const uint8_t* sk, const uint8_t* r, uint8_t* pk, uint8_t* nullifier,
+                            uint8_t* c, uint8_t* s_out, uint8_t* r_point, uint8_t* hashed_to_curve_r, uint8_t* status,
+                            void* stream) {
+    if (!ctx) return PLUME_E_ARG;
+    if (version != 1 && version != 2) return fail(ctx, PLUME_E_ARG, "version must be 1 or 2");
+    if (n == 0) return PLUME_OK;
+    if (n > ctx->chunk) return fail(ctx, PLUME_E_ARG, "n exceeds plume_ctx_chunk_items()");
+    if (!sk || !r || !pk || !nullifier || !c || !s_out || !status) return fail(ctx, PLUME_E_ARG, "null array");
+    ScopedDevice sd(ctx->device);
+    sign_args a;
+    a.version = version; a.n = (uint32_t)n;
+    a.msgs.base = msgs; a.msgs.offs = msg_offsets; a.msgs.fixed_len = (uint32_t)msg_len;
+    a.sk = sk; a.r = r; a.pk = pk; a.nullifier = nullifier; a.c = c; a.s = s_out;
+    a.r_point = r_point; a.hashed_to_curve_r = hashed_to_curve_r; a.status = status;
+    a.ws = ctx->lanes[0].ws; a.gtab = ctx->gtab; a.gw = ctx->gw;
+    return enqueue_sign(ctx, a, (cudaStream_t)stream);
+}
+
+int plume_verify_batch_device(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets,
+                              size_t msg_len, const uint8_t* pk, const uint8_t* nullifier, const uint8_t* c,
+                              const uint8_t* s_in, const uint8_t* r_point, const uint8_t* hashed_to_curve_r, uint8_t* ok,
+                              void* stream) {
+    if (!ctx) return PLUME_E_ARG;
+    if (version != 1 && version != 2) return fail(ctx, PLUME_E_ARG, "version must be 1 or 2");
+    if (n == 0) return PLUME_OK;
+    if (n > ctx->chunk) return fail(ctx, PLUME_E_ARG, "n exceeds plume_ctx_chunk_items()");
+    if (!pk || !nullifier || !c || !s_in || !ok) return fail(ctx, PLUME_E_ARG, "null array");
+    if (version == 1 && (!r_point || !hashed_to_curve_r)) return fail(ctx, PLUME_E_ARG, "V1 needs r_point and hashed_to_curve_r");
+    ScopedDevice sd(ctx->device);
+    verify_args a;
+    a.version = version; a.n = (uint32_t)n;
+    a.msgs.base = msgs; a.msgs.offs = msg_offsets; a.msgs.fixed_len = (uint32_t)msg_len;
+    a.pk = pk; a.nullifier = nullifier; a.c = c; a.s = s_in; a.r_point = r_point; a.hashed_to_curve_r = hashed_to_curve_r;
+    a.ok = ok; a.ws = ctx->lanes[0].ws; a.gtab = ctx->gtab; a.gw = ctx->gw;
+    return enqueue_verify(ctx, a, (cudaStream_t)stream);
+}
+
+int plume_hash_to_curve_batch_device(plume_ctx* ctx, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets,
+                                     size_t msg_len, uint8_t* out, void* stream) {
+    if (!ctx) return PLUME_E_ARG;
+    if (n == 0) return PLUME_OK;
+    if (n > ctx->chunk) return fail(ctx, PLUME_E_ARG, "n exceeds plume_ctx_chunk_items()");
+    if (!out) return fail(ctx, PLUME_E_ARG, "null array");
+    ScopedDevice sd(ctx->device);
+    h2c_args a;
+    a.n = (uint32_t)n;
+    a.msgs.base = msgs; a.msgs.offs = msg_offsets; a.msgs.fixed_len = (uint32_t)msg_len;
+    a.out = out; a.ws = ctx->lanes[0].ws;
+    return enqueue_h2c(ctx, a, (cudaStream_t)stream);
+}
+
+// ---- host-pointer variants: chunked, two lanes in flight --------------------------------------------------------
+int plume_sign_batch(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets,
+                     size_t msg_len, const uint8_t* sk, const uint8_t* r, uint8_t* pk, uint8_t* nullifier, uint8_t* c,
+                     uint8_t* s_out, uint8_t* r_point, uint8_t* hashed_to_curve_r, uint8_t* status) {
+    if (int rc = check_common(ctx, n, msgs, msg_offsets, msg_len)) return rc;
+    if (version != 1 && version != 2) return fail(ctx, PLUME_E_ARG, "version must be 1 or 2");
+    if (n == 0) return PLUME_OK;
+    if (!sk || !r || !pk || !nullifier || !c || !s_out || !status) return fail(ctx, PLUME_E_ARG, "null array");
+    ScopedDevice sd(ctx->device);
+    size_t k = 0;
+    for (size_t i0 = 0; i0 < n; i0 += ctx->chunk, k++) {
+        const size_t cn = (n - i0 < ctx->chunk) ? n - i0 : ctx->chunk;
+        Lane& L = ctx->lanes[k & 1];
+        if (int rc = lane_finish(ctx, L)) return rc;
+        if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * (64 + 64 * 4 + 64 + 1) + 4096)) return rc;
+        L.d_io_used = 0;
+        L.busy = true;
+        sign_args a;
+        a.version = version; a.n = (uint32_t)cn;
+        if (int rc = lane_msgs(ctx, L, msgs, msg_offsets, msg_len, i0, cn, &a.msgs)) return rc;
+        uint8_t *d_sk, *d_r;
+        if (int rc = lane_input(ctx, L, sk + i0 * 32, cn * 32, &d_sk)) return rc;
+        if (int rc = lane_input(ctx, L, r + i0 * 32, cn * 32, &d_r)) return rc;
+        a.sk = d_sk; a.r = d_r;
+        size_t o_pk, o_nul, o_c, o_s, o_rp = 0, o_hr = 0, o_st;
+        a.pk = lane_output(L, cn * 64, &o_pk);
+        a.nullifier = lane_output(L, cn * 64, &o_nul);
+        a.c = lane_output(L, cn * 32, &o_c);
+        a.s = lane_output(L, cn * 32, &o_s);
+        a.r_point = r_point ? lane_output(L, cn * 64, &o_rp) : nullptr;
+        a.hashed_to_curve_r = hashed_to_curve_r ? lane_output(L, cn * 64, &o_hr) : nullptr;
+        a.status = lane_output(L, cn, &o_st);
+        a.ws = L.ws; a.gtab = ctx->gtab; a.gw = ctx->gw;
+        if (int rc = enqueue_sign(ctx, a, L.stream)) return rc;
+        if (int rc = lane_fetch(ctx, L, pk + i0 * 64, o_pk, cn * 64)) return rc;
+        if (int rc = lane_fetch(ctx, L, nullifier + i0 * 64, o_nul, cn * 64)) return rc;
+        if (int rc = lane_fetch(ctx, L, c + i0 * 32, o_c, cn * 32)) return rc;
+        if (int rc = lane_fetch(ctx, L, s_out + i0 * 32, o_s, cn * 32)) return rc;
+        if (r_point) if (int rc = lane_fetch(ctx, L, r_point + i0 * 64, o_rp, cn * 64)) return rc;
+        if (hashed_to_curve_r) if (int rc = lane_fetch(ctx, L, hashed_to_curve_r + i0 * 64, o_hr, cn * 64)) return rc;
+        if (int rc = lane_fetch(ctx, L, status + i0, o_st, cn)) return rc;
+    }
+    for (Lane& L : ctx->lanes) if (int rc = lane_finish(ctx, L)) return rc;
+    return PLUME_OK;
+}
+
+int plume_verify_batch(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets,
+                       size_t msg_len, const uint8_t* pk, const uint8_t* nullifier, const uint8_t* c, const uint8_t* s_in,
+                       const uint8_t* r_point, const uint8_t* hashed_to_curve_r, uint8_t* ok) {
+    if (int rc = check_common(ctx, n, msgs, msg_offsets, msg_len)) return rc;
+    if (version != 1 && version != 2) return fail(ctx, PLUME_E_ARG, "version must be 1 or 2");
+    if (n == 0) return PLUME_OK;
+    if (!pk || !nullifier || !c || !s_in || !ok) return fail(ctx, PLUME_E_ARG, "null array");
+    if (version == 1 && (!r_point || !hashed_to_curve_r)) return fail(ctx, PLUME_E_ARG, "V1 needs r_point and hashed_to_curve_r");
+    ScopedDevice sd(ctx->device);
+    size_t k = 0;
+    for (size_t i0 = 0; i0 < n; i0 += ctx->chunk, k++) {
+        const size_t cn = (n - i0 < ctx->chunk) ? n - i0 : ctx->chunk;
+        Lane& L = ctx->lanes[k & 1];
+        if (int rc = lane_finish(ctx, L)) return rc;
+        if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * (64 * 4 + 64 + 1) + 4096)) return rc;
+        L.d_io_used = 0;
+        L.busy = true;
+        verify_args a;
+        a.version = version; a.n = (uint32_t)cn;
+        if (int rc = lane_msgs(ctx, L, msgs, msg_offsets, msg_len, i0, cn, &a.msgs)) return rc;
+        uint8_t *d_pk, *d_nul, *d_c, *d_s, *d_rp = nullptr, *d_hr = nullptr;
+        if (int rc = lane_input(ctx, L, pk + i0 * 64, cn * 64, &d_pk)) return rc;
+        if (int rc = lane_input(ctx, L, nullifier + i0 * 64, cn * 64, &d_nul)) return rc;
+        if (int rc = lane_input(ctx, L, c + i0 * 32, cn * 32, &d_c)) return rc;
+        if (int rc = lane_input(ctx, L, s_in + i0 * 32, cn * 32, &d_s)) return rc;
+        if (version == 1) {
+            if (int rc = lane_input(ctx, L, r_point + i0 * 64, cn * 64, &d_rp)) return rc;
+            if (int rc = lane_input(ctx, L, hashed_to_curve_r + i0 * 64, cn * 64, &d_hr)) return rc;
+        }
+        a.pk = d_pk; a.nullifier = d_nul; a.c = d_c; a.s = d_s; a.r_point = d_rp; a.hashed_to_curve_r = d_hr;
+        size_t o_ok;
+        a.ok = lane_output(L, cn, &o_ok);
+        a.ws = L.ws; a.gtab = ctx->gtab; a.gw = ctx->gw;
+        if (int rc = enqueue_verify(ctx, a, L.stream)) return rc;
+        if (int rc = lane_fetch(ctx, L, ok + i0, o_ok, cn)) return rc;
+    }
+    for (Lane& L : ctx->lanes) if (int rc = lane_finish(ctx, L)) return rc;
+    return PLUME_OK;
+}
+
+int plume_hash_to_curve_batch(plume_ctx* ctx, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                              uint8_t* out) {
+    if (int rc = check_common(ctx, n, msgs, msg_offsets, msg_len)) return rc;
+    if (n == 0) return PLUME_OK;
+    if (!out) return fail(ctx, PLUME_E_ARG, "null array");
+    ScopedDevice sd(ctx->device);
+    size_t k = 0;
+    for (size_t i0 = 0; i0 < n; i0 += ctx->chunk, k++) {
+        const size_t cn = (n - i0 < ctx->chunk) ? n - i0 : ctx->chunk;
+        Lane& L = ctx->lanes[k & 1];
+        if (int rc = lane_finish(ctx, L)) return rc;
+        if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * 64 + 4096)) return rc;
+        L.d_io_used = 0;
+        L.busy = true;
+        h2c_args a;
+        a.n = (uint32_t)cn;
+        if (int rc = lane_msgs(ctx, L, msgs, msg_offsets, msg_len, i0, cn, &a.msgs)) return rc;
+        size_t o_out;
+        a.out = lane_output(L, cn * 64, &o_out);
+        a.ws = L.ws;
+        if (int rc = enqueue_h2c(ctx, a, L.stream)) return rc;
+        if (int rc = lane_fetch(ctx, L, out + i0 * 64, o_out, cn * 64)) return rc;
+    }
+    for (Lane& L : ctx->lanes) if (int rc = lane_finish(ctx, L)) return rc;
+    return PLUME_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+// ec.cuh -- secp256k1 group law (y^2 = x^3 + 7) in Jacobian coordinates, SEC1 helpers.
+//
+// Replaces k256::ProjectivePoint / AffinePoint arithmetic that the reference calls at
+// rust-k256/src/randomizedsigner.rs:51,53,67,70 (scalar multiplications) and
+// rust-k256/src/lib.rs:101,109 (the verifier's two mul-sub combinations); generator per
+// rust-arkworks/src/secp256k1/curves/mod.rs:50-58.
+//
+// All formulas are complete for the inputs they can meet here: the exceptional cases of the
+// addition (P + P, P + (-P), identity operands) branch to the right answer instead of assuming
+// they cannot happen, because a verifier is fed adversarial points and scalars.
+#pragma once
+#include "fe.cuh"
+
+struct aff { fe x, y; uint32_t inf; };
+struct jac { fe x, y, z; uint32_t inf; };
+
+PLUME_DEV fe fe_lit(uint32_t w7, uint32_t w6, uint32_t w5, uint32_t w4, uint32_t w3, uint32_t w2, uint32_t w1, uint32_t w0) {
+    fe r;
+    r.v[0] = w0; r.v[1] = w1; r.v[2] = w2; r.v[3] = w3; r.v[4] = w4; r.v[5] = w5; r.v[6] = w6; r.v[7] = w7;
+    return r;
+}
+PLUME_DEV fe ec_gx() { return fe_lit(0x79BE667Eu, 0xF9DCBBACu, 0x55A06295u, 0xCE870B07u, 0x029BFCDBu, 0x2DCE28D9u, 0x59F2815Bu, 0x16F81798u); }
+PLUME_DEV fe ec_gy() { return fe_lit(0x483ADA77u, 0x26A3C465u, 0x5DA4FBFCu, 0x0E1108A8u, 0xFD17B448u, 0xA6855419u, 0x9C47D08Fu, 0xFB10D4B8u); }
+// beta: cube root of unity in Fp with lambda*(x, y) = (beta*x, y)
+PLUME_DEV fe ec_beta() { return fe_lit(0x7AE96A2Bu, 0x657C0710u, 0x6E64479Eu, 0xAC3434E9u, 0x9CF04975u, 0x12F58995u, 0xC1396C28u, 0x719501EEu); }
+
+PLUME_DEV jac jac_infinity() { jac r; r.x = fe_zero(); r.y = fe_zero(); r.z = fe_zero(); r.inf = 1; return r; }
+PLUME_DEV aff aff_infinity() { aff r; r.x = fe_zero(); r.y = fe_zero(); r.inf = 1; return r; }
+PLUME_DEV jac jac_from_aff(const aff& p) { jac r; r.x = p.x; r.y = p.y; r.z = fe_one(); r.inf = p.inf; return r; }
+
+// y^2 == x^3 + 7 ?
+PLUME_DEV bool aff_on_curve(const fe& x, const fe& y) {
+    fe lhs = fe_sqr(y);
+    fe rhs = fe_add(fe_mul(fe_sqr(x), x), fe_set_u32(7));
+    return fe_eq(lhs, rhs);
+}
+
+// 2P, a = 0: 2M + 5S  (no point of order two exists: the group order is odd)
+PLUME_DEV jac jac_dbl(const jac& p) {
+    if (p.inf) return p;
+    fe A = fe_sqr(p.x);
+    fe B = fe_sqr(p.y);
+    fe C = fe_sqr(B);
+    fe t = fe_sqr(fe_add(p.x, B));
+    fe D = fe_dbl(fe_sub(fe_sub(t, A), C));
+    fe E = fe_add(fe_dbl(A), A);
+    fe F = fe_sqr(E);
+    jac r;
+    r.x = fe_sub(F, fe_dbl(D));
+    fe C8 = fe_dbl(fe_dbl(fe_dbl(C)));
+    r.y = fe_sub(fe_mul(E, fe_sub(D, r.x)), C8);
+    r.z = fe_dbl(fe_mul(p.y, p.z));
+    r.inf = 0;
+    return r;
+}
+
+// P + Q, Q affine: 8M + 3S.  `zscale` (optional out) receives H so that Z3 = Z1 * H.
+PLUME_DEV jac jac_add_aff(const jac& p, const fe& qx, const fe& qy, uint32_t qinf) {
+    if (qinf) return p;
+    if (p.inf) { jac r; r.x = qx; r.y = qy; r.z = fe_one(); r.inf = 0; return r; }
+    fe z2 = fe_sqr(p.z);
+    fe u2 = fe_mul(qx, z2);
+    fe s2 = fe_mul(qy, fe_mul(p.z, z2));
+    fe H = fe_sub(u2, p.x);
+    fe R = fe_sub(s2, p.y);
+    if (fe_is_zero(H)) {
+        if (fe_is_zero(R)) return jac_dbl(p);
+        return jac_infinity();
+    }
+    fe H2 = fe_sqr(H);
+    fe H3 = fe_mul(H, H2);
+    fe V = fe_mul(p.x, H2);
+    jac r;
+    r.x = fe_sub(fe_sub(fe_sqr(R), H3), fe_dbl(V));
+    r.y = fe_sub(fe_mul(R, fe_sub(V, r.x)), fe_mul(p.y, H3));
+    r.z = fe_mul(p.z, H);
+    r.inf = 0;
+    return r;
+}
+
+// P + Q, both Jacobian: 12M + 4S
+PLUME_DEV jac jac_add(const jac& p, const jac& q) {
+    if (q.inf) return p;
+    if (p.inf) return q;
+    fe z1z1 = fe_sqr(p.z), z2z2 = fe_sqr(q.z);
+    fe u1 = fe_mul(p.x, z2z2), u2 = fe_mul(q.x, z1z1);
+    fe s1 = fe_mul(p.y, fe_mul(q.z, z2z2)), s2 = fe_mul(q.y, fe_mul(p.z, z1z1));
+    fe H = fe_sub(u2, u1);
+    fe R = fe_sub(s2, s1);
+    if (fe_is_zero(H)) {
+        if (fe_is_zero(R)) return jac_dbl(p);
+        return jac_infinity();
+    }
+    fe H2 = fe_sqr(H);
+    fe H3 = fe_mul(H, H2);
+    fe V = fe_mul(u1, H2);
+    jac r;
+    r.x = fe_sub(fe_sub(fe_sqr(R), H3), fe_dbl(V));
+    r.y = fe_sub(fe_mul(R, fe_sub(V, r.x)), fe_mul(s1, H3));
+    r.z = fe_mul(fe_mul(p.z, q.z), H);
+    r.inf = 0;
+    return r;
+}
+
+PLUME_DEV jac jac_neg(const jac& p) { jac r = p; r.y = fe_neg(p.y); return r; }
+
+// affine from Jacobian given zinv = 1/Z (canonical coordinates)
+PLUME_DEV aff aff_from_jac_zinv(const jac& p, const fe& zinv) {
+    aff r;
+    if (p.inf) return aff_infinity();
+    fe zi2 = fe_sqr(zinv);
+    r.x = fe_norm(fe_mul(p.x, zi2));
+    r.y = fe_norm(fe_mul(p.y, fe_mul(zi2, zinv)));
+    r.inf = 0;
+    return r;
+}
+
+// affine (canonical) equality including the identity
+PLUME_DEV bool aff_eq(const aff& a, const aff& b) {
+    if (a.inf || b.inf) return (a.inf != 0) == (b.inf != 0);
+    return fe_eq(a.x, b.x) && fe_eq(a.y, b.y);
+}

@@ -1,0 +1,42 @@
+// k_sign.cu -- stage kernels of the signing pipeline (bodies in stages.cuh).
+#include "launch.h"
+
+__global__ void __launch_bounds__(128) k_sign_fixed(sign_args a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) sign_stage_fixed(i, a);
+}
+__global__ void __launch_bounds__(128) k_sign_h2c(sign_args a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) sign_stage_h2c(i, a);
+}
+__global__ void __launch_bounds__(VB_BLOCK) k_sign_varbase(sign_args a) {
+    extern __shared__ uint32_t vb_smem[];
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) sign_stage_varbase(i, a, vb_smem + threadIdx.x, VB_BLOCK);
+}
+__global__ void __launch_bounds__(128) k_sign_final(sign_args a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) sign_stage_final(i, a);
+}
+
+static inline unsigned grid_for(uint32_t n, unsigned b) { return (n + b - 1) / b; }
+
+cudaError_t launch_sign_fixed(const sign_args& a, cudaStream_t s) {
+    k_sign_fixed<<<grid_for(a.n, 128), 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_sign_h2c(const sign_args& a, cudaStream_t s) {
+    k_sign_h2c<<<grid_for(a.n, 128), 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_sign_varbase(const sign_args& a, cudaStream_t s) {
+    k_sign_varbase<<<grid_for(a.n, VB_BLOCK), VB_BLOCK, VB_SMEM_BYTES, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_sign_final(const sign_args& a, cudaStream_t s) {
+    k_sign_final<<<grid_for(a.n, 128), 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t kernels_init_sign() {
+    return cudaFuncSetAttribute(k_sign_varbase, cudaFuncAttributeMaxDynamicSharedMemorySize, VB_SMEM_BYTES);
+}

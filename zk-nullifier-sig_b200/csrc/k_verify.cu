@@ -1,0 +1,34 @@
+// k_verify.cu -- stage kernels of the verification pipeline (bodies in stages.cuh).
+#include "launch.h"
+
+__global__ void __launch_bounds__(128) k_verify_h2c(verify_args a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) verify_stage_h2c(i, a);
+}
+__global__ void __launch_bounds__(VB_BLOCK) k_verify_muls(verify_args a) {
+    extern __shared__ uint32_t vb_smem[];
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) verify_stage_muls(i, a, vb_smem + threadIdx.x, VB_BLOCK);
+}
+__global__ void __launch_bounds__(128) k_verify_final(verify_args a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) verify_stage_final(i, a);
+}
+
+static inline unsigned grid_for(uint32_t n, unsigned b) { return (n + b - 1) / b; }
+
+cudaError_t launch_verify_h2c(const verify_args& a, cudaStream_t s) {
+    k_verify_h2c<<<grid_for(a.n, 128), 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_verify_muls(const verify_args& a, cudaStream_t s) {
+    k_verify_muls<<<grid_for(a.n, VB_BLOCK), VB_BLOCK, VB_SMEM_BYTES, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_verify_final(const verify_args& a, cudaStream_t s) {
+    k_verify_final<<<grid_for(a.n, 128), 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t kernels_init_verify() {
+    return cudaFuncSetAttribute(k_verify_muls, cudaFuncAttributeMaxDynamicSharedMemorySize, VB_SMEM_BYTES);
+}

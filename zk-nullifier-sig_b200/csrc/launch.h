@@ -1,0 +1,29 @@
+// launch.h -- host-side launchers of the stage kernels (one translation unit per kernel family so
+// that nvcc compiles them in parallel).  Every launcher enqueues on `stream` and returns the
+// cudaError_t of the launch.
+#pragma once
+#include <cuda_runtime.h>
+#include "stages.cuh"
+
+// threads per block of the kernels that keep a per-thread table in shared memory
+#define VB_BLOCK 128
+#define VB_SMEM_BYTES (VB_TAB_WORDS * 4 * VB_BLOCK)
+
+cudaError_t launch_sign_fixed(const sign_args& a, cudaStream_t s);
+cudaError_t launch_sign_h2c(const sign_args& a, cudaStream_t s);
+cudaError_t launch_sign_varbase(const sign_args& a, cudaStream_t s);
+cudaError_t launch_sign_final(const sign_args& a, cudaStream_t s);
+cudaError_t launch_verify_h2c(const verify_args& a, cudaStream_t s);
+cudaError_t launch_verify_muls(const verify_args& a, cudaStream_t s);
+cudaError_t launch_verify_final(const verify_args& a, cudaStream_t s);
+cudaError_t launch_h2c_map(const h2c_args& a, cudaStream_t s);
+cudaError_t launch_h2c_out(const h2c_args& a, cudaStream_t s);
+// batched inversion of m elements at Z (scratch same size), `per_thread` elements per thread
+cudaError_t launch_binv(uint32_t* Z, uint32_t* scratch, uint32_t m, uint32_t per_thread, cudaStream_t s);
+// generator table
+cudaError_t launch_gtab_bases(uint32_t* bases, int w, cudaStream_t s);
+cudaError_t launch_gtab_entries(uint32_t ne, uint32_t* tab, uint32_t* zs, const uint32_t* bases, int w, cudaStream_t s);
+cudaError_t launch_gtab_norm(uint32_t ne, uint32_t* tab, const uint32_t* zs, cudaStream_t s);
+// integer-pipe microbenchmark: every thread runs `iters` * 64 independent-chain IMAD.WIDE.U32
+cudaError_t launch_imad_peak(uint32_t* sink, int iters, int blocks, int threads, cudaStream_t s);
+cudaError_t kernels_init();  // opt-in shared memory sizes

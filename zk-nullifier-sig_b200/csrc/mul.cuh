@@ -1,0 +1,134 @@
+// mul.cuh -- scalar multiplication: fixed-base (generator, precomputed table in HBM/L2) and
+// variable-base (GLV + signed radix-16 windows over a per-thread co-Z table in shared memory).
+//
+// One thread owns one scalar multiplication; all threads of a warp add at the same loop step
+// (fixed windows instead of NAF), so the warp never serialises on data-dependent add/skip
+// decisions.  Replaces `ProjectivePoint * Scalar` / `NonIdentity * NonZeroScalar` of k256
+// (rust-k256/src/randomizedsigner.rs:51,53,67,70; rust-k256/src/lib.rs:101,109).
+#pragma once
+#include "ec.cuh"
+#include "sc.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// Fixed base.  gtab holds, for window j (w bits each) and digit d in [1, 2^w), the affine point
+// d * 2^(w*j) * G as 16 words (x limbs then y limbs) at index (j << w) + d.
+// ---------------------------------------------------------------------------------------------
+PLUME_DEV jac fb_mul(const sc& k, const uint32_t* gtab, int w) {
+    uint32_t s[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i] = k.v[i];
+    const int nwin = (256 + w - 1) / w;
+    const uint32_t mask = (1u << w) - 1;
+    jac acc = jac_infinity();
+#pragma unroll 1
+    for (int j = 0; j < nwin; j++) {
+        uint32_t d = s[0] & mask;
+        // s >>= w
+#pragma unroll
+        for (int i = 0; i < 7; i++) s[i] = (s[i] >> w) | (s[i + 1] << (32 - w));
+        s[7] >>= w;
+        if (d != 0) {
+            const uint32_t* e = gtab + (((size_t)j << w) + d) * 16;
+            fe qx, qy;
+#ifdef PLUME_HOSTSIM
+            for (int i = 0; i < 8; i++) { qx.v[i] = e[i]; qy.v[i] = e[8 + i]; }
+#else
+            const uint4* e4 = reinterpret_cast<const uint4*>(e);
+            uint4 a = __ldg(e4), b = __ldg(e4 + 1), c = __ldg(e4 + 2), dd = __ldg(e4 + 3);
+            qx.v[0] = a.x; qx.v[1] = a.y; qx.v[2] = a.z; qx.v[3] = a.w; qx.v[4] = b.x; qx.v[5] = b.y; qx.v[6] = b.z; qx.v[7] = b.w;
+            qy.v[0] = c.x; qy.v[1] = c.y; qy.v[2] = c.z; qy.v[3] = c.w; qy.v[4] = dd.x; qy.v[5] = dd.y; qy.v[6] = dd.z; qy.v[7] = dd.w;
+#endif
+            acc = jac_add_aff(acc, qx, qy, 0);
+        }
+    }
+    return acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Variable base.  Per-thread table of 1P .. 8P, all brought to the common denominator Zg = Z(8P)
+// ("co-Z": the entries are affine points of the isomorphic curve y^2 = x^3 + 7*Zg^6, on which the
+// a = 0 doubling/addition formulas are unchanged), so the main loop uses the cheap mixed addition
+// without any inversion; the result's Z is multiplied by Zg at the end.
+// Table word (entry e in 0..7, word i in 0..15) lives at tab[(e*16 + i) * stride].
+// ---------------------------------------------------------------------------------------------
+#define VB_TAB_WORDS 128
+
+PLUME_DEV void vb_tab_store(uint32_t* tab, int stride, int e, const fe& x, const fe& y) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        tab[(e * 16 + i) * stride] = x.v[i];
+        tab[(e * 16 + 8 + i) * stride] = y.v[i];
+    }
+}
+PLUME_DEV void vb_tab_load(const uint32_t* tab, int stride, int e, fe& x, fe& y) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        x.v[i] = tab[(e * 16 + i) * stride];
+        y.v[i] = tab[(e * 16 + 8 + i) * stride];
+    }
+}
+
+// builds the table for the affine, on-curve, non-identity point (px, py); returns Zg
+PLUME_DEV fe vb_build_table(const fe& px, const fe& py, uint32_t* tab, int stride) {
+    fe hs[8];  // hs[k] = Z_{k+1} / Z_k, k = 1..7 (local memory; touched 14 times per table)
+    jac cur;
+    cur.x = px; cur.y = py; cur.z = fe_one(); cur.inf = 0;
+    vb_tab_store(tab, stride, 0, px, py);
+    cur = jac_dbl(cur);
+    hs[1] = cur.z;
+    vb_tab_store(tab, stride, 1, cur.x, cur.y);
+#pragma unroll 1
+    for (int k = 2; k < 8; k++) {
+        // cur = k*P (Jacobian) ; next = cur + P ; Z_next = Z_cur * H with H = px*Z^2 - X
+        fe z2 = fe_sqr(cur.z);
+        fe H = fe_sub(fe_mul(px, z2), cur.x);
+        cur = jac_add_aff(cur, px, py, 0);
+        hs[k] = H;
+        vb_tab_store(tab, stride, k, cur.x, cur.y);
+    }
+    fe zg = cur.z;
+    fe ratio = fe_one();
+#pragma unroll 1
+    for (int k = 7; k >= 1; k--) {
+        ratio = fe_mul(ratio, hs[k]);  // Z_8 / Z_k
+        fe x, y;
+        vb_tab_load(tab, stride, k - 1, x, y);
+        fe r2 = fe_sqr(ratio);
+        x = fe_mul(x, r2);
+        y = fe_mul(y, fe_mul(r2, ratio));
+        vb_tab_store(tab, stride, k - 1, x, y);
+    }
+    return zg;
+}
+
+// acc += d * T  (d in [-8, 8], `flip` negates, `endo` applies (x, y) -> (beta*x, y))
+PLUME_DEV jac vb_add_digit(const jac& acc, int d, uint32_t flip, bool endo, const uint32_t* tab, int stride) {
+    if (d == 0) return acc;
+    uint32_t neg = (d < 0 ? 1u : 0u) ^ flip;
+    int e = (d < 0 ? -d : d) - 1;
+    fe x, y;
+    vb_tab_load(tab, stride, e, x, y);
+    if (endo) x = fe_mul(x, ec_beta());
+    fe ny = fe_neg(y);
+    y = fe_cmov(y, ny, neg != 0);
+    return jac_add_aff(acc, x, y, 0);
+}
+
+// k * P from the prepared table; k canonical in [0, n)
+PLUME_DEV jac vb_mul_tab(const sc& k, const uint32_t* tab, int stride, const fe& zg) {
+    glv_half h1, h2;
+    glv_split(k, h1, h2);
+    booth_reg b1 = booth_init(h1), b2 = booth_init(h2);
+    jac acc = jac_infinity();
+#pragma unroll 1
+    for (int i = 32; i >= 0; i--) {
+#pragma unroll 1
+        for (int j = 0; j < 4; j++) acc = jac_dbl(acc);
+        int d1 = booth_next(b1);
+        int d2 = booth_next(b2);
+        acc = vb_add_digit(acc, d1, h1.neg, false, tab, stride);
+        acc = vb_add_digit(acc, d2, h2.neg, true, tab, stride);
+    }
+    if (!acc.inf) acc.z = fe_mul(acc.z, zg);
+    return acc;
+}

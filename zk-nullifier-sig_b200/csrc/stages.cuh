@@ -1,0 +1,506 @@
+// stages.cuh -- per-item bodies of the pipeline stages.  Each kernel in kernels.cu is
+// `i = global thread id; if (i < n) stage_body(i, args)`; the host-sim test build loops the same
+// bodies on the CPU.  Between stages the per-item state lives in HBM as structure-of-arrays
+// "slots" of 32-byte field elements (8 little-endian limbs), so every access is a pair of
+// coalesced 128-bit loads/stores, and the only field inversions are done by the batched
+// inversion stage over a contiguous Z array.
+//
+// Sign   (rust-k256/src/randomizedsigner.rs:43-112):
+//   S1 fixed-base  g^r, g^sk            -> Jacobian                     [sign_stage_fixed]
+//   BI batched inversion of the 2 Z's
+//   S2 affine R, pk; pk33; h = H2C(m || pk33) -> Jacobian               [sign_stage_h2c]
+//   BI batched inversion of Z_h
+//   S3 affine h; co-Z table of h; h^r, h^sk -> Jacobian                 [sign_stage_varbase]
+//   BI batched inversion of the 2 Z's
+//   S4 affine z, nul; c = SHA-256(...); s = r + c*sk; outputs + status   [sign_stage_final]
+// Verify (rust-k256/src/lib.rs:93-145):
+//   V1 input checks; h = H2C(m || enc(pk)) -> Jacobian                  [verify_stage_h2c]
+//   BI
+//   V2 A = s*G - c*pk ; B = s*h - c*nul -> Jacobian                      [verify_stage_muls]
+//   BI
+//   V3 affine A, B; (V1: compare with r_point, hashed_to_curve_r); c == SHA-256(...) mod n  [verify_stage_final]
+#pragma once
+#include "h2c.cuh"
+#include "mul.cuh"
+
+// ---- status codes (include/plume_b200.h) ---------------------------------------------------------
+#define PLUME_ST_OK 0
+#define PLUME_ST_BAD_R 1
+#define PLUME_ST_BAD_SK 2
+#define PLUME_ST_BAD_C 3
+#define PLUME_ST_ZERO_S 4
+#define PLUME_ST_H_INF 5
+
+// ---- 32-byte element I/O ---------------------------------------------------------------------------
+PLUME_DEV fe ld_fe(const uint32_t* p) {
+    fe r;
+#ifdef PLUME_HOSTSIM
+    for (int i = 0; i < 8; i++) r.v[i] = p[i];
+#else
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+#endif
+    return r;
+}
+PLUME_DEV void st_fe(uint32_t* p, const fe& a) {
+#ifdef PLUME_HOSTSIM
+    for (int i = 0; i < 8; i++) p[i] = a.v[i];
+#else
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    q[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+#endif
+}
+// 32 big-endian bytes (16-byte aligned) -> limbs, and back
+PLUME_DEV fe ld_fe_be(const uint8_t* p) {
+    uint32_t w[8];
+#ifdef PLUME_HOSTSIM
+    for (int i = 0; i < 8; i++) w[i] = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) | ((uint32_t)p[4 * i + 3] << 24);
+#else
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+#endif
+    return fe_from_be_words(w);  // bswap per word + word reversal
+}
+PLUME_DEV void st_fe_be(uint8_t* p, const fe& a) {
+    uint32_t w[8];
+    fe_to_be_words(w, a);
+#ifdef PLUME_HOSTSIM
+    for (int i = 0; i < 8; i++) { p[4 * i] = (uint8_t)w[i]; p[4 * i + 1] = (uint8_t)(w[i] >> 8); p[4 * i + 2] = (uint8_t)(w[i] >> 16); p[4 * i + 3] = (uint8_t)(w[i] >> 24); }
+#else
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+#endif
+}
+PLUME_DEV sc ld_sc_be(const uint8_t* p) {
+    fe t = ld_fe_be(p);
+    sc r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = t.v[i];
+    return r;
+}
+PLUME_DEV void st_sc_be(uint8_t* p, const sc& a) {
+    fe t;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t.v[i] = a.v[i];
+    st_fe_be(p, t);
+}
+PLUME_DEV void st_zero32(uint8_t* p) { st_fe_be(p, fe_zero()); }
+
+// a >= p ?  (wire coordinates must be canonical, as k256's AffinePoint decoding requires)
+PLUME_DEV bool fe_ge_p(const fe& a) {
+    fe n = fe_norm(a);
+    uint32_t d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) d |= n.v[i] ^ a.v[i];
+    return d != 0;
+}
+
+// wire point (x || y, 64 bytes; 64 zero bytes = identity) -> aff; returns false if malformed
+PLUME_DEV bool ld_point_be(aff& p, const uint8_t* src) {
+    p.x = ld_fe_be(src);
+    p.y = ld_fe_be(src + 32);
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= p.x.v[i] | p.y.v[i];
+    p.inf = (o == 0);
+    if (p.inf) return true;
+    if (fe_ge_p(p.x) || fe_ge_p(p.y)) return false;
+    return aff_on_curve(p.x, p.y);
+}
+PLUME_DEV void st_point_be(uint8_t* dst, const aff& p) {
+    if (p.inf) { st_zero32(dst); st_zero32(dst + 32); return; }
+    st_fe_be(dst, p.x);
+    st_fe_be(dst + 32, p.y);
+}
+
+// ---- messages ----------------------------------------------------------------------------------------
+struct msg_view {
+    const uint8_t* base;
+    const uint64_t* offs;  // n+1 offsets, or null for fixed-length records
+    uint32_t fixed_len;
+};
+PLUME_DEV const uint8_t* msg_ptr(const msg_view& m, uint32_t i, uint32_t& len) {
+    if (m.offs) {
+        uint64_t a = m.offs[i], b = m.offs[i + 1];
+        len = (uint32_t)(b - a);
+        return m.base + a;
+    }
+    len = m.fixed_len;
+    return m.base + (size_t)i * m.fixed_len;
+}
+
+// SEC1 compressed encoding into a byte buffer; returns the length (33, or 1 for the identity)
+// (rust-k256/src/utils.rs:23-25)
+PLUME_DEV uint32_t enc_point33(uint8_t* out, const aff& p) {
+    if (p.inf) { out[0] = 0; return 1; }
+    out[0] = (uint8_t)(2 + (p.y.v[0] & 1));
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t w = p.x.v[7 - i];
+        out[1 + 4 * i] = (uint8_t)(w >> 24);
+        out[2 + 4 * i] = (uint8_t)(w >> 16);
+        out[3 + 4 * i] = (uint8_t)(w >> 8);
+        out[4 + 4 * i] = (uint8_t)w;
+    }
+    return 33;
+}
+PLUME_DEV void sha_put_point(sha256_stream& s, const aff& p) {
+    if (p.inf) { sha256_stream_byte(s, 0); return; }
+    sha256_stream_byte(s, (uint8_t)(2 + (p.y.v[0] & 1)));
+#pragma unroll 1
+    for (int i = 7; i >= 0; i--) sha256_stream_word(s, p.x.v[i]);
+}
+PLUME_DEV aff aff_generator() { aff g; g.x = ec_gx(); g.y = ec_gy(); g.inf = 0; return g; }
+
+// c = SHA-256(enc(G) || enc(pk) || enc(h) || enc(nul) || enc(R) || enc(z))  (V1)
+//   = SHA-256(enc(nul) || enc(R) || enc(z))                                  (V2)
+// rust-k256/src/lib.rs:159-168, rust-k256/src/randomizedsigner.rs:73-89
+PLUME_DEV sc plume_challenge(int version, const aff& pk, const aff& h, const aff& nul, const aff& R, const aff& z) {
+    sha256_stream s;
+    sha256_init(s.st);
+    s.fill = 0;
+    s.total = 0;
+    if (version == 1) {
+        sha_put_point(s, aff_generator());
+        sha_put_point(s, pk);
+        sha_put_point(s, h);
+    }
+    sha_put_point(s, nul);
+    sha_put_point(s, R);
+    sha_put_point(s, z);
+    uint32_t d[8];
+    sha256_stream_final(s, d);
+    sc c;
+#pragma unroll
+    for (int i = 0; i < 8; i++) c.v[i] = d[7 - i];
+    return c;
+}
+
+// ---- workspace ---------------------------------------------------------------------------------------
+// slot s, item i  ->  ws + (s * n + i) * 8 words
+PLUME_DEV uint32_t* ws_at(uint32_t* ws, uint32_t n, int slot, uint32_t i) { return ws + ((size_t)slot * n + i) * 8; }
+
+// slots shared by sign / verify / h2c pipelines
+enum {
+    WS_Z0 = 0, WS_Z1 = 1,        // contiguous Z array fed to the batched inversion (2n elements)
+    WS_P0 = 2, WS_P1 = 3,        // prefix-product scratch of the batched inversion
+    WS_AX = 4, WS_AY = 5,        // Jacobian X, Y of point A (sign: R = g^r, later z = h^r; verify: A)
+    WS_BX = 6, WS_BY = 7,        // Jacobian X, Y of point B (sign: pk, later nul; verify: B)
+    WS_HX = 8, WS_HY = 9,        // h: Jacobian X, Y, then affine x, y
+    WS_RX = 10, WS_RY = 11,      // sign: affine R
+    WS_KX = 12, WS_KY = 13,      // sign: affine pk
+    WS_SLOTS = 14
+};
+
+struct sign_args {
+    int version;
+    uint32_t n;
+    msg_view msgs;
+    const uint8_t* sk;    // n x 32 BE
+    const uint8_t* r;     // n x 32 BE
+    uint8_t* pk;          // n x 64
+    uint8_t* nullifier;   // n x 64
+    uint8_t* c;           // n x 32
+    uint8_t* s;           // n x 32
+    uint8_t* r_point;     // n x 64 or null
+    uint8_t* hashed_to_curve_r;  // n x 64 or null
+    uint8_t* status;      // n
+    uint32_t* ws;
+    const uint32_t* gtab;
+    int gw;
+};
+
+PLUME_DEV sc sc_one() { sc r; for (int i = 0; i < 8; i++) r.v[i] = (i == 0); return r; }
+
+PLUME_DEV void sign_stage_fixed(uint32_t i, const sign_args& a) {
+    sc r = ld_sc_be(a.r + (size_t)i * 32);
+    sc sk = ld_sc_be(a.sk + (size_t)i * 32);
+    uint8_t st = PLUME_ST_OK;
+    if (!sc_is_valid_nonzero(sk)) { st = PLUME_ST_BAD_SK; sk = sc_one(); }
+    if (!sc_is_valid_nonzero(r)) { st = PLUME_ST_BAD_R; r = sc_one(); }
+    a.status[i] = st;
+    jac R = fb_mul(r, a.gtab, a.gw);
+    st_fe(ws_at(a.ws, a.n, WS_AX, i), R.x);
+    st_fe(ws_at(a.ws, a.n, WS_AY, i), R.y);
+    st_fe(ws_at(a.ws, a.n, WS_Z0, i), R.z);
+    jac K = fb_mul(sk, a.gtab, a.gw);
+    st_fe(ws_at(a.ws, a.n, WS_BX, i), K.x);
+    st_fe(ws_at(a.ws, a.n, WS_BY, i), K.y);
+    st_fe(ws_at(a.ws, a.n, WS_Z1, i), K.z);
+}
+
+PLUME_DEV aff ws_load_affine(uint32_t* ws, uint32_t n, int sx, int sy, int sz, uint32_t i) {
+    jac p;
+    p.x = ld_fe(ws_at(ws, n, sx, i));
+    p.y = ld_fe(ws_at(ws, n, sy, i));
+    fe zinv = ld_fe(ws_at(ws, n, sz, i));
+    p.z = zinv;
+    p.inf = fe_is_zero(zinv);  // the inversion stage maps Z = 0 (identity) to 0
+    return aff_from_jac_zinv(p, zinv);
+}
+PLUME_DEV void ws_store_jac(uint32_t* ws, uint32_t n, int sx, int sy, int sz, uint32_t i, const jac& p) {
+    st_fe(ws_at(ws, n, sx, i), p.x);
+    st_fe(ws_at(ws, n, sy, i), p.y);
+    st_fe(ws_at(ws, n, sz, i), p.inf ? fe_zero() : p.z);
+}
+PLUME_DEV void ws_store_aff(uint32_t* ws, uint32_t n, int sx, int sy, uint32_t i, const aff& p) {
+    st_fe(ws_at(ws, n, sx, i), p.x);
+    st_fe(ws_at(ws, n, sy, i), p.y);
+}
+
+PLUME_DEV void sign_stage_h2c(uint32_t i, const sign_args& a) {
+    aff R = ws_load_affine(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i);
+    aff K = ws_load_affine(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i);
+    ws_store_aff(a.ws, a.n, WS_RX, WS_RY, i, R);
+    ws_store_aff(a.ws, a.n, WS_KX, WS_KY, i, K);
+    uint8_t pk33[33];
+    uint32_t npk = enc_point33(pk33, K);
+    uint32_t len;
+    const uint8_t* m = msg_ptr(a.msgs, i, len);
+    jac h = h2c_hash_to_curve(m, len, pk33, npk);
+    ws_store_jac(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i, h);
+}
+
+// tab: this thread's table (stride = distance in words between consecutive table words)
+PLUME_DEV void sign_stage_varbase(uint32_t i, const sign_args& a, uint32_t* tab, int stride) {
+    aff h = ws_load_affine(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i);
+    ws_store_aff(a.ws, a.n, WS_HX, WS_HY, i, h);
+    if (h.inf) {
+        // the reference panics here (randomizedsigner.rs:61); flag it and leave identity results
+        a.status[i] = PLUME_ST_H_INF;
+        jac o = jac_infinity();
+        ws_store_jac(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i, o);
+        ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, o);
+        return;
+    }
+    fe zg = vb_build_table(h.x, h.y, tab, stride);
+    sc r = ld_sc_be(a.r + (size_t)i * 32);
+    sc sk = ld_sc_be(a.sk + (size_t)i * 32);
+    if (!sc_is_valid_nonzero(sk)) sk = sc_one();
+    if (!sc_is_valid_nonzero(r)) r = sc_one();
+#pragma unroll 1
+    for (int which = 0; which < 2; which++) {
+        jac o = vb_mul_tab(which == 0 ? r : sk, tab, stride, zg);
+        if (which == 0) ws_store_jac(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i, o);
+        else ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, o);
+    }
+}
+
+PLUME_DEV void sign_stage_final(uint32_t i, const sign_args& a) {
+    aff z = ws_load_affine(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i);
+    aff nul = ws_load_affine(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i);
+    aff h, R, K;
+    h.x = ld_fe(ws_at(a.ws, a.n, WS_HX, i)); h.y = ld_fe(ws_at(a.ws, a.n, WS_HY, i)); h.inf = 0;
+    R.x = ld_fe(ws_at(a.ws, a.n, WS_RX, i)); R.y = ld_fe(ws_at(a.ws, a.n, WS_RY, i)); R.inf = 0;
+    K.x = ld_fe(ws_at(a.ws, a.n, WS_KX, i)); K.y = ld_fe(ws_at(a.ws, a.n, WS_KY, i)); K.inf = 0;
+    uint8_t st = a.status[i];
+    sc c = plume_challenge(a.version, K, h, nul, R, z);
+    sc s = sc_one();
+    if (st == PLUME_ST_OK) {
+        if (!sc_is_valid_nonzero(c)) {
+            st = PLUME_ST_BAD_C;  // NonZeroScalar::from_repr(c).expect (randomizedsigner.rs:90-91)
+        } else {
+            sc r = ld_sc_be(a.r + (size_t)i * 32);
+            sc sk = ld_sc_be(a.sk + (size_t)i * 32);
+            s = sc_add(r, sc_mul(c, sk));  // randomizedsigner.rs:94
+            if (sc_is_zero(s)) st = PLUME_ST_ZERO_S;
+        }
+    }
+    a.status[i] = st;
+    const bool ok = (st == PLUME_ST_OK);
+    aff none = aff_infinity();
+    st_point_be(a.pk + (size_t)i * 64, ok ? K : none);
+    st_point_be(a.nullifier + (size_t)i * 64, ok ? nul : none);
+    if (ok) { st_sc_be(a.c + (size_t)i * 32, c); st_sc_be(a.s + (size_t)i * 32, s); }
+    else { st_zero32(a.c + (size_t)i * 32); st_zero32(a.s + (size_t)i * 32); }
+    if (a.r_point) st_point_be(a.r_point + (size_t)i * 64, ok ? R : none);
+    if (a.hashed_to_curve_r) st_point_be(a.hashed_to_curve_r + (size_t)i * 64, ok ? z : none);
+}
+
+// ---- batched inversion ---------------------------------------------------------------------------------
+// Z[0..m) in place -> 1/Z (0 stays 0).  Thread t of T owns elements t, t+T, t+2T, ... (coalesced),
+// multiplies them into a running product, inverts once, and walks back (Montgomery's trick):
+// 3 multiplications per element + one ~270-multiplication inversion per K elements.
+PLUME_DEV void binv_body(uint32_t t, uint32_t T, uint32_t* Z, uint32_t* scratch, uint32_t m) {
+    fe acc = fe_one();
+    uint32_t cnt = 0;
+#pragma unroll 1
+    for (uint32_t idx = t; idx < m; idx += T, cnt++) {
+        fe z = ld_fe(Z + (size_t)idx * 8);
+        st_fe(scratch + (size_t)idx * 8, acc);
+        if (!fe_is_zero(z)) acc = fe_mul(acc, z);
+    }
+    if (cnt == 0) return;
+    fe inv = fe_inv(acc);
+#pragma unroll 1
+    for (uint32_t j = cnt; j-- > 0;) {
+        uint32_t idx = t + j * T;
+        fe z = ld_fe(Z + (size_t)idx * 8);
+        if (fe_is_zero(z)) { st_fe(Z + (size_t)idx * 8, fe_zero()); continue; }
+        fe pre = ld_fe(scratch + (size_t)idx * 8);
+        st_fe(Z + (size_t)idx * 8, fe_mul(inv, pre));
+        inv = fe_mul(inv, z);
+    }
+}
+
+// ---- verify -----------------------------------------------------------------------------------------------
+struct verify_args {
+    int version;
+    uint32_t n;
+    msg_view msgs;
+    const uint8_t* pk;         // n x 64
+    const uint8_t* nullifier;  // n x 64
+    const uint8_t* c;          // n x 32
+    const uint8_t* s;          // n x 32
+    const uint8_t* r_point;    // n x 64 (V1)
+    const uint8_t* hashed_to_curve_r;  // n x 64 (V1)
+    uint8_t* ok;               // n
+    uint32_t* ws;
+    const uint32_t* gtab;
+    int gw;
+};
+
+// ok[i] is used as scratch between stages: 1 = inputs well-formed so far, 0 = reject
+PLUME_DEV void verify_stage_h2c(uint32_t i, const verify_args& a) {
+    aff pk, nul;
+    bool good = ld_point_be(pk, a.pk + (size_t)i * 64);
+    good = ld_point_be(nul, a.nullifier + (size_t)i * 64) && good;
+    sc c = ld_sc_be(a.c + (size_t)i * 32), s = ld_sc_be(a.s + (size_t)i * 32);
+    good = good && sc_is_valid_nonzero(c) && sc_is_valid_nonzero(s);  // NonZeroScalar fields
+    if (a.version == 1) {
+        aff t;
+        good = ld_point_be(t, a.r_point + (size_t)i * 64) && good;
+        good = ld_point_be(t, a.hashed_to_curve_r + (size_t)i * 64) && good;
+    }
+    a.ok[i] = good ? 1 : 0;
+    if (!good) pk = aff_generator();  // keep the lane on the common path; result is discarded
+    uint8_t pk33[33];
+    uint32_t npk = enc_point33(pk33, pk);
+    uint32_t len;
+    const uint8_t* m = msg_ptr(a.msgs, i, len);
+    jac h = h2c_hash_to_curve(m, len, pk33, npk);  // lib.rs:103
+    ws_store_jac(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i, h);
+}
+
+// k * P for an affine P that may be the identity
+PLUME_DEV jac vb_mul_point(const aff& p, const sc& k, uint32_t* tab, int stride) {
+    if (p.inf) return jac_infinity();
+    fe zg = vb_build_table(p.x, p.y, tab, stride);
+    return vb_mul_tab(k, tab, stride, zg);
+}
+
+PLUME_DEV void verify_stage_muls(uint32_t i, const verify_args& a, uint32_t* tab, int stride) {
+    aff h = ws_load_affine(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i);
+    ws_store_aff(a.ws, a.n, WS_HX, WS_HY, i, h);
+    // remember whether h is the identity: WS_RX limb 0
+    st_fe(ws_at(a.ws, a.n, WS_RX, i), fe_set_u32(h.inf));
+    aff pk, nul;
+    bool good = a.ok[i] != 0;
+    sc c = sc_one(), s = sc_one();
+    if (good) {
+        ld_point_be(pk, a.pk + (size_t)i * 64);
+        ld_point_be(nul, a.nullifier + (size_t)i * 64);
+        c = ld_sc_be(a.c + (size_t)i * 32);
+        s = ld_sc_be(a.s + (size_t)i * 32);
+    } else {
+        pk = aff_generator();
+        nul = aff_generator();
+    }
+    sc mc = sc_neg(c);
+    // A = G*s - pk*c   (lib.rs:101)
+    jac A = fb_mul(s, a.gtab, a.gw);
+    A = jac_add(A, vb_mul_point(pk, mc, tab, stride));
+    ws_store_jac(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i, A);
+    // B = h*s - nul*c  (lib.rs:109)
+    jac B = vb_mul_point(h, s, tab, stride);
+    B = jac_add(B, vb_mul_point(nul, mc, tab, stride));
+    ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, B);
+}
+
+PLUME_DEV void verify_stage_final(uint32_t i, const verify_args& a) {
+    bool good = a.ok[i] != 0;
+    if (!good) { a.ok[i] = 0; return; }
+    aff A = ws_load_affine(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i);
+    aff B = ws_load_affine(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i);
+    aff h;
+    h.x = ld_fe(ws_at(a.ws, a.n, WS_HX, i));
+    h.y = ld_fe(ws_at(a.ws, a.n, WS_HY, i));
+    h.inf = ld_fe(ws_at(a.ws, a.n, WS_RX, i)).v[0];
+    aff pk, nul;
+    ld_point_be(pk, a.pk + (size_t)i * 64);
+    ld_point_be(nul, a.nullifier + (size_t)i * 64);
+    if (a.version == 1) {
+        aff rs, zs;
+        ld_point_be(rs, a.r_point + (size_t)i * 64);
+        ld_point_be(zs, a.hashed_to_curve_r + (size_t)i * 64);
+        if (!aff_eq(A, rs)) { a.ok[i] = 0; return; }   // lib.rs:117
+        if (!aff_eq(B, zs)) { a.ok[i] = 0; return; }   // lib.rs:122
+    }
+    sc d = sc_reduce256(plume_challenge(a.version, pk, h, nul, A, B));  // lib.rs:127-143
+    sc c = ld_sc_be(a.c + (size_t)i * 32);
+    a.ok[i] = sc_eq(c, d) ? 1 : 0;
+}
+
+// ---- hash_to_curve only (rust-k256/src/utils.rs:11-20 with the preimage supplied by the caller) ----------
+struct h2c_args {
+    uint32_t n;
+    msg_view msgs;            // the full preimage (PLUME: m || enc33(pk))
+    uint8_t* out;             // n x 64 affine (zeros = identity)
+    uint32_t* ws;
+};
+PLUME_DEV void h2c_stage_map(uint32_t i, const h2c_args& a) {
+    uint32_t len;
+    const uint8_t* m = msg_ptr(a.msgs, i, len);
+    jac h = h2c_hash_to_curve(m, len, m, 0);
+    ws_store_jac(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i, h);
+}
+PLUME_DEV void h2c_stage_out(uint32_t i, const h2c_args& a) {
+    aff h = ws_load_affine(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i);
+    st_point_be(a.out + (size_t)i * 64, h);
+}
+
+// ---- generator table construction (once per context) -------------------------------------------------------
+// bases[j] = 2^(w*j) * G, affine, 16 words each
+PLUME_DEV void gtab_bases_body(uint32_t* bases, int w) {
+    const int nwin = (256 + w - 1) / w;
+    jac cur;
+    cur.x = ec_gx(); cur.y = ec_gy(); cur.z = fe_one(); cur.inf = 0;
+#pragma unroll 1
+    for (int j = 0; j < nwin; j++) {
+        fe zi = fe_inv(cur.z);
+        aff p = aff_from_jac_zinv(cur, zi);
+        st_fe(bases + j * 16, p.x);
+        st_fe(bases + j * 16 + 8, p.y);
+#pragma unroll 1
+        for (int k = 0; k < w; k++) cur = jac_dbl(cur);
+    }
+}
+// entry e = (j << w) + d: Jacobian d * bases[j] -> tab (X, Y) and Zs[e]
+PLUME_DEV void gtab_entry_body(uint32_t e, uint32_t* tab, uint32_t* zs, const uint32_t* bases, int w) {
+    uint32_t j = e >> w, d = e & ((1u << w) - 1);
+    fe bx = ld_fe(bases + j * 16), by = ld_fe(bases + j * 16 + 8);
+    jac acc = jac_infinity();
+#pragma unroll 1
+    for (int b = w - 1; b >= 0; b--) {
+        acc = jac_dbl(acc);
+        if ((d >> b) & 1) acc = jac_add_aff(acc, bx, by, 0);
+    }
+    st_fe(tab + (size_t)e * 16, acc.x);
+    st_fe(tab + (size_t)e * 16 + 8, acc.y);
+    st_fe(zs + (size_t)e * 8, acc.inf ? fe_zero() : acc.z);
+}
+PLUME_DEV void gtab_norm_body(uint32_t e, uint32_t* tab, const uint32_t* zs) {
+    jac p;
+    p.x = ld_fe(tab + (size_t)e * 16);
+    p.y = ld_fe(tab + (size_t)e * 16 + 8);
+    fe zi = ld_fe(zs + (size_t)e * 8);
+    p.z = zi;
+    p.inf = fe_is_zero(zi);
+    aff q = aff_from_jac_zinv(p, zi);
+    st_fe(tab + (size_t)e * 16, q.x);
+    st_fe(tab + (size_t)e * 16 + 8, q.y);
+}

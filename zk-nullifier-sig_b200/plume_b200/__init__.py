@@ -1,0 +1,10 @@
+"""plume_b200 -- B200-native batch PLUME signer/verifier: Python host mirror of plume_rustcrypto's
+API over the C ABI in include/plume_b200.h (CUDA kernels for sm_100a in ../csrc)."""
+from .api import (DST, ORDER, PlumeContext, PlumeError, PlumeSignature, PlumeSignatureV1Fields, PlumeSigner,
+                  SecretKey, default_context, encode_pt, hash_to_curve, pack_messages, point_from_bytes,
+                  point_to_bytes)
+from ._lib import LIB_PATH, SYMBOLS, load
+
+__all__ = ["DST", "ORDER", "PlumeContext", "PlumeError", "PlumeSignature", "PlumeSignatureV1Fields", "PlumeSigner",
+           "SecretKey", "default_context", "encode_pt", "hash_to_curve", "pack_messages", "point_from_bytes",
+           "point_to_bytes", "LIB_PATH", "SYMBOLS", "load"]

@@ -1,0 +1,286 @@
+"""Host-side mirror of the reference's operator interface for the PLUME hot path, over the C ABI.
+
+Reference (Rust, crate `plume_rustcrypto`, /root/reference/rust-k256):
+  PlumeSignature{message, pk, nullifier, c, s, v1specific}        src/lib.rs:67-80
+  PlumeSignatureV1Fields{r_point, hashed_to_curve_r}              src/lib.rs:84-89
+  PlumeSignature::verify / sign_v1 / sign_v2                      src/lib.rs:93,149,154
+  PlumeSigner::new + try_sign_with_rng                            src/randomizedsigner.rs:38,43
+  DST                                                             src/lib.rs:61
+
+Same names, argument meaning and error behaviour; the batch entry points are the additions.
+Points are (x, y) tuples of ints or None for the identity; scalars are ints.  All compute goes
+through libplume_b200.so on the GPU -- there is no Python/CPU implementation in this package.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+DST = b"QUUX-V01-CS02-with-secp256k1_XMD:SHA-256_SSWU_RO_"  # rust-k256/src/lib.rs:61
+ORDER = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+
+STATUS_TEXT = {  # the `expect` messages of the reference at the places it panics
+    1: "nonce r outside [1, n-1]",
+    2: "secret key outside [1, n-1]",
+    3: "it should be impossible to get the hash equal to zero",                      # randomizedsigner.rs:91
+    4: "something is terribly wrong if the nonce is equal to negated product of the secret and the hash",  # :95
+    5: "something is drammatically wrong if the input hashed to the identity",       # :61
+}
+
+
+class PlumeError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def _as_u8(a, shape=None):
+    a = np.ascontiguousarray(np.frombuffer(a, dtype=np.uint8) if isinstance(a, (bytes, bytearray)) else a, dtype=np.uint8)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def pack_messages(msgs):
+    """list of bytes -> (blob u8[total], offsets u64[n+1])"""
+    offs = np.zeros(len(msgs) + 1, dtype=np.uint64)
+    if msgs:
+        offs[1:] = np.cumsum([len(m) for m in msgs], dtype=np.uint64)
+    blob = np.frombuffer(b"".join(msgs), dtype=np.uint8) if msgs else np.zeros(0, dtype=np.uint8)
+    return np.ascontiguousarray(blob), offs
+
+
+class PlumeContext:
+    """One GPU's signer/verifier (plume_ctx_create).  One context per process per GPU."""
+
+    def __init__(self, device=0, fixed_window_bits=0):
+        self._lib = _lib.load()
+        h = ctypes.c_void_p()
+        rc = self._lib.plume_ctx_create(ctypes.byref(h), int(device), int(fixed_window_bits))
+        if rc != 0:
+            raise PlumeError("plume_ctx_create failed (%d): %s" % (rc, self._lib.plume_last_error(None).decode()))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.plume_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise PlumeError("%s failed (%d): %s" % (what, rc, self._lib.plume_last_error(self._h).decode()))
+
+    @property
+    def chunk_items(self):
+        return self._lib.plume_ctx_chunk_items(self._h)
+
+    @property
+    def launch_count(self):
+        return self._lib.plume_ctx_launch_count(self._h)
+
+    def set_profiling(self, on):
+        self._check(self._lib.plume_ctx_set_profiling(self._h, 1 if on else 0), "plume_ctx_set_profiling")
+
+    def stage_ms(self, stage):
+        n = ctypes.c_uint64(0)
+        ms = self._lib.plume_ctx_stage_ms(self._h, stage.encode(), ctypes.byref(n))
+        return ms, n.value
+
+    def measure_imad_peak(self, iters=4096):
+        v = ctypes.c_double(0)
+        self._check(self._lib.plume_measure_imad_peak(self._h, iters, ctypes.byref(v)), "plume_measure_imad_peak")
+        return v.value
+
+    # ---- batch entry points on host (numpy) buffers ---------------------------------------------------
+    @staticmethod
+    def _msgs(msgs, msg_len):
+        """msgs: list of bytes | (blob, offsets) | u8 array [n, msg_len]"""
+        if isinstance(msgs, (list, tuple)) and (len(msgs) == 0 or isinstance(msgs[0], (bytes, bytearray))):
+            blob, offs = pack_messages(list(msgs))
+            return blob, offs, 0, len(msgs)
+        if isinstance(msgs, tuple):
+            blob, offs = msgs
+            return _as_u8(blob), np.ascontiguousarray(offs, dtype=np.uint64), 0, len(offs) - 1
+        a = _as_u8(msgs)
+        if a.ndim != 2:
+            raise ValueError("fixed-length messages must be a [n, msg_len] u8 array")
+        return a, None, a.shape[1], a.shape[0]
+
+    def sign_batch(self, version, msgs, sk, r, out=None):
+        """plume_sign_batch.  sk, r: u8[n,32] big-endian.  Returns dict of u8 arrays + status."""
+        blob, offs, mlen, n = self._msgs(msgs, None)
+        sk = _as_u8(sk, (n, 32))
+        r = _as_u8(r, (n, 32))
+        o = out or {}
+        for k, w in (("pk", 64), ("nullifier", 64), ("c", 32), ("s", 32), ("r_point", 64), ("hashed_to_curve_r", 64)):
+            if k not in o:
+                o[k] = np.empty((n, w), dtype=np.uint8)
+        if "status" not in o:
+            o["status"] = np.empty(n, dtype=np.uint8)
+        rc = self._lib.plume_sign_batch(self._h, version, n, _ptr(blob), _ptr(offs), mlen, _ptr(sk), _ptr(r),
+                                        _ptr(o["pk"]), _ptr(o["nullifier"]), _ptr(o["c"]), _ptr(o["s"]),
+                                        _ptr(o["r_point"]), _ptr(o["hashed_to_curve_r"]), _ptr(o["status"]))
+        self._check(rc, "plume_sign_batch")
+        return o
+
+    def verify_batch(self, version, msgs, pk, nullifier, c, s, r_point=None, hashed_to_curve_r=None, out=None):
+        blob, offs, mlen, n = self._msgs(msgs, None)
+        pk = _as_u8(pk, (n, 64)); nullifier = _as_u8(nullifier, (n, 64))
+        c = _as_u8(c, (n, 32)); s = _as_u8(s, (n, 32))
+        rp = None if r_point is None else _as_u8(r_point, (n, 64))
+        hr = None if hashed_to_curve_r is None else _as_u8(hashed_to_curve_r, (n, 64))
+        ok = out if out is not None else np.empty(n, dtype=np.uint8)
+        rc = self._lib.plume_verify_batch(self._h, version, n, _ptr(blob), _ptr(offs), mlen, _ptr(pk), _ptr(nullifier),
+                                          _ptr(c), _ptr(s), _ptr(rp), _ptr(hr), _ptr(ok))
+        self._check(rc, "plume_verify_batch")
+        return ok
+
+    def hash_to_curve_batch(self, msgs, out=None):
+        blob, offs, mlen, n = self._msgs(msgs, None)
+        o = out if out is not None else np.empty((n, 64), dtype=np.uint8)
+        rc = self._lib.plume_hash_to_curve_batch(self._h, n, _ptr(blob), _ptr(offs), mlen, _ptr(o))
+        self._check(rc, "plume_hash_to_curve_batch")
+        return o
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = PlumeContext(0)
+    return _default_ctx
+
+
+# ---- conversions -----------------------------------------------------------------------------------------
+def point_to_bytes(p):
+    return bytes(64) if p is None else p[0].to_bytes(32, "big") + p[1].to_bytes(32, "big")
+
+
+def point_from_bytes(b):
+    b = bytes(b)
+    if b == bytes(64):
+        return None
+    return (int.from_bytes(b[:32], "big"), int.from_bytes(b[32:], "big"))
+
+
+def encode_pt(p):
+    """SEC1 compressed (rust-k256/src/utils.rs:23-25)."""
+    return b"\x00" if p is None else bytes([2 + (p[1] & 1)]) + p[0].to_bytes(32, "big")
+
+
+# ---- the reference's types ----------------------------------------------------------------------------------
+class PlumeSignatureV1Fields:
+    """rust-k256/src/lib.rs:84-89"""
+
+    def __init__(self, r_point, hashed_to_curve_r):
+        self.r_point = r_point
+        self.hashed_to_curve_r = hashed_to_curve_r
+
+
+class SecretKey:
+    """k256::SecretKey as the reference uses it: a scalar in [1, n-1] (`from_bytes` rejects the rest);
+    `random(rng)` = 32 bytes from rng.fill_bytes, big-endian, rejection-sampled (pinned by the mock
+    RNG of rust-k256/tests/signing.rs:23-44)."""
+
+    def __init__(self, value):
+        if not (1 <= value < ORDER):
+            raise ValueError("secret key out of range")
+        self.value = value
+
+    @classmethod
+    def from_bytes(cls, b):
+        return cls(int.from_bytes(bytes(b), "big"))
+
+    @classmethod
+    def random(cls, rng):
+        while True:
+            buf = bytearray(32)
+            rng.fill_bytes(buf)
+            v = int.from_bytes(buf, "big")
+            if 1 <= v < ORDER:
+                return cls(v)
+
+    def to_bytes(self):
+        return self.value.to_bytes(32, "big")
+
+
+class PlumeSigner:
+    """rust-k256/src/randomizedsigner.rs:25-41: a borrowed secret key + the variant flag."""
+
+    def __init__(self, secret_key, v1, ctx=None):
+        self.secret_key = secret_key
+        self.v1 = v1
+        self._ctx = ctx
+
+    def try_sign_with_rng(self, rng, msg):
+        """randomizedsigner.rs:43-112 as a batch of one."""
+        r = SecretKey.random(rng)                                           # :49
+        ctx = self._ctx or default_context()
+        o = ctx.sign_batch(1 if self.v1 else 2, [bytes(msg)], self.secret_key.to_bytes(), r.to_bytes())
+        st = int(o["status"][0])
+        if st != 0:
+            raise PlumeError(STATUS_TEXT.get(st, "status %d" % st))         # the reference panics here
+        v1f = None
+        if self.v1:
+            v1f = PlumeSignatureV1Fields(point_from_bytes(o["r_point"][0]), point_from_bytes(o["hashed_to_curve_r"][0]))
+        return PlumeSignature(bytes(msg), point_from_bytes(o["pk"][0]), point_from_bytes(o["nullifier"][0]),
+                              int.from_bytes(bytes(o["c"][0]), "big"), int.from_bytes(bytes(o["s"][0]), "big"), v1f, ctx=ctx)
+
+    sign_with_rng = try_sign_with_rng
+
+
+class PlumeSignature:
+    """rust-k256/src/lib.rs:67-80"""
+
+    def __init__(self, message, pk, nullifier, c, s, v1specific=None, ctx=None):
+        self.message = bytes(message)
+        self.pk = pk
+        self.nullifier = nullifier
+        self.c = c
+        self.s = s
+        self.v1specific = v1specific
+        self._ctx = ctx
+
+    def verify(self):
+        """rust-k256/src/lib.rs:93-145 as a batch of one."""
+        ctx = self._ctx or default_context()
+        v1 = self.v1specific
+        ok = ctx.verify_batch(1 if v1 else 2, [self.message], point_to_bytes(self.pk), point_to_bytes(self.nullifier),
+                              self.c.to_bytes(32, "big"), self.s.to_bytes(32, "big"),
+                              point_to_bytes(v1.r_point) if v1 else None,
+                              point_to_bytes(v1.hashed_to_curve_r) if v1 else None)
+        return bool(ok[0])
+
+    @staticmethod
+    def sign_v1(secret_key, msg, rng, ctx=None):
+        """rust-k256/src/lib.rs:149-151"""
+        return PlumeSigner(secret_key, True, ctx).sign_with_rng(rng, msg)
+
+    @staticmethod
+    def sign_v2(secret_key, msg, rng, ctx=None):
+        """rust-k256/src/lib.rs:154-156"""
+        return PlumeSigner(secret_key, False, ctx).sign_with_rng(rng, msg)
+
+
+def hash_to_curve(m, pk, ctx=None):
+    """rust-k256/src/utils.rs:11-20"""
+    ctx = ctx or default_context()
+    return point_from_bytes(ctx.hash_to_curve_batch([bytes(m) + encode_pt(pk)])[0])
