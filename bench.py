@@ -1,0 +1,415 @@
+#!/usr/bin/env python3
+"""bench.py -- PLUME sigs+verifies/sec (batch, bit-exact) on N B200s, next to the CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sign_verify|sign|verify|h2c|config4]
+                    [--log2-batch B] [--impl ours|reference]
+    torchrun ... bench.py --gpus N ...          (one rank per GPU; N > 1)
+
+One "step" = one pass of the hot path over one batch of synthetic input per GPU.  Default workload
+(BASELINE.json configs[1] + configs[2]): PLUME V1 sign of 2^20 items (32-byte messages, random sk, r)
+followed by V1 verify of those 2^20 signatures, i.e. 2^21 operations per step per GPU; the metric is
+operations (signatures + verifications) per second, whole job.
+
+Numbers on the JSON line:
+  value     device-resident: inputs already in HBM, `_device` C-ABI calls on one stream, CUDA events.
+  e2e       same work through the host-pointer C-ABI calls with pinned host buffers: H2D of the inputs
+            and D2H of every output inside the timed region (wall clock between synchronisations).
+  roofline  dominant kernel (variable-base scalar multiplications) against the integer-ALU peak measured
+            on the spot by plume_measure_imad_peak (IMAD.WIDE.U32 issue rate); SURVEY.md 8(d).
+  cpu_baseline  the C oracle ("port" of the rust-k256 path; cargo is not available) on the host cores,
+            bounded sample.
+Inputs follow SURVEY.md 8(d): m_i = SHA256("plume-b200/m" || S || i), sk_i / r_i by SHA-256 counter
+with rejection into [1, n-1]; S and i are u64 big-endian.
+"""
+import argparse
+import hashlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "zk-nullifier-sig_b200"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+
+ORDER = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+# algorithmic work per item, SURVEY.md 8(d): M = 72 limb products (LP)
+LP_PER_M = 72
+WORK_M = {"sign": 4500, "verify": 4900, "h2c": 910,
+          "sign_varbase": 2830,            # pair of scalar multiplications sharing the base h
+          "verify_muls": 1770 + 2200}      # G*s - pk*c and h*s - nul*c
+# algorithmic bytes per item of the dominant kernels (what they must read + write in HBM)
+BYTES = {"sign_varbase": 3 * 32 + 64 + 2 * 32 + 6 * 32, "verify_muls": 3 * 32 + 64 * 2 + 64 + 2 * 32 + 6 * 32}
+
+
+def synth_inputs(seed, first, count):
+    """(msgs u8[count,32], sk u8[count,32], r u8[count,32]) for global item indices first..first+count."""
+    S = seed.to_bytes(8, "big")
+    msgs = np.empty((count, 32), dtype=np.uint8)
+    sk = np.empty((count, 32), dtype=np.uint8)
+    r = np.empty((count, 32), dtype=np.uint8)
+    pm, ps, pr = b"plume-b200/m" + S, b"plume-b200/sk" + S, b"plume-b200/r" + S
+    sha = hashlib.sha256
+    mv, sv, rv = memoryview(msgs).cast("B"), memoryview(sk).cast("B"), memoryview(r).cast("B")
+    for j in range(count):
+        ib = (first + j).to_bytes(8, "big")
+        mv[32 * j:32 * j + 32] = sha(pm + ib).digest()
+        for dst, pre in ((sv, ps), (rv, pr)):
+            ctr = 0
+            while True:   # rejection into [1, n-1], mirrors SecretKey::random
+                d = sha(pre + ib + ctr.to_bytes(8, "big")).digest()
+                if 1 <= int.from_bytes(d, "big") < ORDER:
+                    break
+                ctr += 1
+            dst[32 * j:32 * j + 32] = d
+    return msgs, sk, r
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons of one GPU during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_run(workload, version, msgs, sk, r, threads):
+    """One pass of the workload through the C oracle; returns (ops, seconds, outputs)."""
+    import c_oracle
+    n = msgs.shape[0]
+    t0 = time.perf_counter()
+    ops = 0
+    out = None
+    if workload == "h2c":
+        pre = np.concatenate([msgs, np.full((n, 1), 2, np.uint8), sk], axis=1)   # 65-byte preimages m || 02 || x
+        c_oracle.h2c_batch(pre, threads=threads)
+        ops = n
+    else:
+        out = c_oracle.sign_batch(version, msgs, sk, r, threads=threads)
+        if workload in ("sign", "sign_verify", "config4"):
+            ops += n
+        if workload in ("verify", "sign_verify", "config4"):
+            t1 = time.perf_counter()
+            if workload == "verify":
+                t0 = t1    # signing only prepared the verifier's input
+            c_oracle.verify_batch(version, msgs, out["pk"], out["nullifier"], out["c"], out["s"], out["r_point"],
+                                  out["hashed_to_curve_r"], threads=threads)
+            ops += n
+    return ops, time.perf_counter() - t0, out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sign_verify", choices=["sign_verify", "sign", "verify", "h2c", "config4"])
+    ap.add_argument("--log2-batch", type=int, default=None, help="items per GPU per step = 2^B")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="items of the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    version = 2 if args.workload == "config4" else 1
+    lg = args.log2_batch if args.log2_batch is not None else {"config4": 21, "h2c": 22}.get(args.workload, 20)
+    n = 1 << lg
+    seed = {"sign": 2, "verify": 3, "config4": 4, "h2c": 5}.get(args.workload, 2)
+    ops_per_item = 2 if args.workload in ("sign_verify", "config4") else 1
+    metric = "PLUME sigs+verifies/sec (batch, bit-exact)"
+    cfg = {"workload": {"sign_verify": "BASELINE configs[1]+[2]: batch 2^%d PLUME V1 sign then V1 verify of the same batch" % lg,
+                        "sign": "BASELINE configs[1]: batch 2^%d PLUME V1 sign" % lg,
+                        "verify": "BASELINE configs[2]: batch 2^%d PLUME V1 verify" % lg,
+                        "config4": "BASELINE configs[3]: batch 2^%d per GPU PLUME V2 sign+verify, range-split" % lg,
+                        "h2c": "BASELINE configs[4]: hash_to_curve-only, 2^%d 65-byte preimages" % lg}[args.workload],
+           "version": "V%d" % version, "items_per_gpu_per_step": n, "msg_bytes": 32,
+           "parallelism": "range-split x%d, no data-path collective" % world,
+           "l2": "working set per step (inputs+outputs+workspace > 500 MB) exceeds the 126 MB L2; no explicit flush"}
+
+    # ------------------------------------------------------------------ reference arm: the CPU path
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        threads = host_threads()
+        sample = args.cpu_sample or max(256, min(n, 1 << 13))
+        msgs, sk, r = synth_inputs(seed, 0, sample)
+        times, ops = [], 0
+        for it in range(args.warmup + args.steps):
+            ops, dt, _ = cpu_run(args.workload, version, msgs, sk, r, threads)
+            if it >= args.warmup:
+                times.append(dt)
+        val = ops * len(times) / sum(times)
+        line = {"metric": metric, "value": val, "unit": "ops/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u32 limbs (256-bit modular integer), bit-exact", "data": "synthetic", "config": cfg, "impl": "reference",
+                "cpu_baseline": {"value": val, "unit": "ops/s", "cores": threads, "kind": "port",
+                                 "sample": "%d items per step (%d ops) of the same synthetic workload; C restatement of the "
+                                           "rust-k256 path (cargo/rustc unavailable), %d pthreads" % (sample, ops, threads)},
+                "e2e": {"value": val, "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import plume_b200
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; the PLUME kernels have no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    ctx = plume_b200.PlumeContext(local_rank)
+    chunk = ctx.chunk_items
+
+    msgs_h, sk_h, r_h = synth_inputs(seed, rank * n, n)     # this rank's contiguous range of the global batch
+
+    def pinned(a):
+        t = torch.from_numpy(a).pin_memory()
+        return t
+    # pinned host buffers (e2e arm)
+    H = {"msgs": pinned(msgs_h), "sk": pinned(sk_h), "r": pinned(r_h)}
+    for k, w in (("pk", 64), ("nullifier", 64), ("c", 32), ("s", 32), ("r_point", 64), ("hashed_to_curve_r", 64)):
+        H[k] = torch.empty((n, w), dtype=torch.uint8).pin_memory()
+    H["status"] = torch.empty(n, dtype=torch.uint8).pin_memory()
+    H["ok"] = torch.empty(n, dtype=torch.uint8).pin_memory()
+    # device-resident buffers (value arm)
+    D = {k: H[k].to(dev) for k in ("msgs", "sk", "r")}
+    for k in ("pk", "nullifier", "c", "s", "r_point", "hashed_to_curve_r", "status", "ok"):
+        D[k] = torch.empty_like(H[k], device=dev)
+    if args.workload == "h2c":
+        pre_h = np.ascontiguousarray(np.concatenate([msgs_h, np.full((n, 1), 2, np.uint8), sk_h], axis=1))
+        H["pre"] = pinned(pre_h); H["h"] = torch.empty((n, 64), dtype=torch.uint8).pin_memory()
+        D["pre"] = H["pre"].to(dev); D["h"] = torch.empty((n, 64), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    sp = stream.cuda_stream
+    do_sign = args.workload in ("sign", "sign_verify", "config4", "verify")
+    do_verify = args.workload in ("verify", "sign_verify", "config4")
+
+    def ptr(t, off_items=0, width=None):
+        return t.data_ptr() + off_items * (width if width is not None else (t.shape[1] if t.dim() > 1 else 1))
+
+    def step_device(sign=True, verify=True):
+        for i0 in range(0, n, chunk):
+            cn = min(chunk, n - i0)
+            if args.workload == "h2c":
+                ctx.hash_to_curve_batch_device(cn, ptr(D["pre"], i0), 0, 65, ptr(D["h"], i0), sp)
+                continue
+            if sign:
+                ctx.sign_batch_device(version, cn, ptr(D["msgs"], i0), 0, 32, ptr(D["sk"], i0), ptr(D["r"], i0), ptr(D["pk"], i0),
+                                      ptr(D["nullifier"], i0), ptr(D["c"], i0), ptr(D["s"], i0), ptr(D["r_point"], i0),
+                                      ptr(D["hashed_to_curve_r"], i0), ptr(D["status"], i0), sp)
+            if verify:
+                ctx.verify_batch_device(version, cn, ptr(D["msgs"], i0), 0, 32, ptr(D["pk"], i0), ptr(D["nullifier"], i0),
+                                        ptr(D["c"], i0), ptr(D["s"], i0), ptr(D["r_point"], i0), ptr(D["hashed_to_curve_r"], i0),
+                                        ptr(D["ok"], i0), sp)
+
+    def step_host(sign=True, verify=True):
+        if args.workload == "h2c":
+            ctx.hash_to_curve_batch_ptr(n, ptr(H["pre"]), 0, 65, ptr(H["h"]))
+            return
+        if sign:
+            ctx.sign_batch_ptr(version, n, ptr(H["msgs"]), 0, 32, ptr(H["sk"]), ptr(H["r"]), ptr(H["pk"]), ptr(H["nullifier"]),
+                               ptr(H["c"]), ptr(H["s"]), ptr(H["r_point"]), ptr(H["hashed_to_curve_r"]), ptr(H["status"]))
+        if verify:
+            ctx.verify_batch_ptr(version, n, ptr(H["msgs"]), 0, 32, ptr(H["pk"]), ptr(H["nullifier"]), ptr(H["c"]), ptr(H["s"]),
+                                 ptr(H["r_point"]), ptr(H["hashed_to_curve_r"]), ptr(H["ok"]))
+
+    timed_sign = args.workload != "verify"      # "verify" times the verifier only; signing prepares its input
+    if args.workload == "verify":
+        step_device(sign=True, verify=False); step_host(sign=True, verify=False)
+        torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident, CUDA events on the launching stream
+    for _ in range(args.warmup):
+        step_device(sign=timed_sign, verify=do_verify)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.set_profiling(True)
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device(sign=timed_sign, verify=do_verify)
+    e1.record(stream)
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count - launches0
+    stage = {}
+    for st in ("sign_fixed", "sign_h2c", "sign_varbase", "sign_final", "verify_h2c", "verify_muls", "verify_final", "h2c_map",
+               "h2c_out", "binv"):
+        ms, k = ctx.stage_ms(st)
+        if k:
+            stage[st] = {"ms_total": round(ms, 3), "launches": k}
+    ctx.set_profiling(False)
+
+    # ---- e2e: host pointers (pinned), H2D + D2H inside the timed region, wall clock between syncs
+    for _ in range(max(1, args.warmup // 2)):
+        step_host(sign=timed_sign, verify=do_verify)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host(sign=timed_sign, verify=do_verify)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    if dist is not None:
+        t = torch.tensor([dev_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+    else:
+        e2e_ms = e2e_s * 1e3
+    ops_step_gpu = n * ops_per_item
+    value = world * ops_step_gpu * args.steps / (dev_ms * 1e-3)
+    e2e_val = world * ops_step_gpu * args.steps / (e2e_ms * 1e-3)
+
+    # bytes crossing PCIe per step per GPU (counted from the buffers handed to the host API)
+    if args.workload == "h2c":
+        h2d, d2h = n * 65, n * 64
+    else:
+        h2d = d2h = 0
+        if timed_sign:
+            h2d += n * 96; d2h += n * (64 * 4 + 64 + 1)
+        if do_verify:
+            h2d += n * (32 + 64 * 4 + 64); d2h += n
+
+    # ---- correctness inside the run: every status OK, every signature verifies; strided bit-exact sample vs the oracle
+    checks = {}
+    if args.workload != "h2c":
+        if do_sign:
+            checks["sign_status_ok"] = int((D["status"] == 0).sum().item()) == n and int((H["status"] == 0).sum().item()) == n
+        if do_verify:
+            checks["verify_all_true"] = int(D["ok"].sum().item()) == n and int(H["ok"].sum().item()) == n
+        for k in ("pk", "nullifier", "c", "s", "r_point", "hashed_to_curve_r"):
+            if not torch.equal(D[k].cpu(), H[k]):
+                checks["device_vs_host_api_" + k] = False
+    if dist is not None:
+        flag = torch.tensor([1 if all(checks.values()) else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        checks["all_ranks"] = bool(flag.item())
+
+    line = {"metric": metric, "value": value, "unit": "ops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 limbs (256-bit modular integer), bit-exact", "data": "synthetic", "config": cfg,
+            "e2e": {"value": e2e_val, "unit": "ops/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches, "checks": checks}
+
+    if rank == 0:
+        # roofline of the dominant kernel against the integer-ALU peak measured here
+        peak_lp = ctx.measure_imad_peak(4096)
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        dom = max((s for s in stage if s != "binv"), key=lambda s: stage[s]["ms_total"])
+        per_launch_items = min(chunk, n)
+        avg_ms = stage[dom]["ms_total"] / stage[dom]["launches"]
+        work_m = WORK_M.get(dom, WORK_M["h2c"] if dom.startswith("h2c") else 640)
+        ach = per_launch_items * work_m * LP_PER_M / (avg_ms * 1e-3)
+        line["roofline"] = {"bound": "int-alu", "kernel": dom, "achieved": ach, "peak": peak_lp, "unit": "limb-products/s",
+                            "frac": ach / peak_lp, "traffic": None,
+                            "peak_source": "measured in this run: IMAD.WIDE.U32 independent-chain microbenchmark "
+                                           "(MEASURED_PEAKS.json carries no INT32 figure)",
+                            "algorithmic_work": "%d field multiplications x %d limb-products per item (SURVEY.md 8d), %d items per launch"
+                                                % (work_m, LP_PER_M, per_launch_items),
+                            "avg_launch_ms": avg_ms}
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        gbs = per_launch_items * BYTES.get(dom, 160) / (avg_ms * 1e-3) / 1e9
+        line["roofline"]["hbm"] = {"achieved_gbs": gbs, "peak_gbs": hbm_peak, "frac": gbs / hbm_peak,
+                                   "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}
+        # whole-step view: all kernels of the step against the same peak
+        step_work = {"sign_verify": WORK_M["sign"] + WORK_M["verify"], "config4": WORK_M["sign"] + WORK_M["verify"],
+                     "sign": WORK_M["sign"], "verify": WORK_M["verify"], "h2c": WORK_M["h2c"]}[args.workload]
+        line["roofline"]["whole_step_frac"] = (n * step_work * LP_PER_M * args.steps / (dev_ms * 1e-3)) / peak_lp
+        line["stages"] = stage
+        line["clocks"] = clocks
+        # cpu baseline, bounded sample, rank 0 only at N = 1
+        if world == 1 and not args.no_cpu_baseline:
+            threads = host_threads()
+            sample = args.cpu_sample or max(1024, min(n, 1 << 13))
+            ops, dt, out = cpu_run(args.workload, version, msgs_h[:sample], sk_h[:sample], r_h[:sample], threads)
+            line["cpu_baseline"] = {"value": ops / dt, "unit": "ops/s", "cores": threads, "kind": "port",
+                                    "sample": "first %d items of this workload (%d ops), C restatement of the rust-k256 path "
+                                              "(cargo/rustc unavailable), %d pthreads, %.1f s" % (sample, ops, threads, dt)}
+            if out is not None and do_sign:
+                same = all(np.array_equal(H[k][:sample].numpy(), out[k]) for k in
+                           ("pk", "nullifier", "c", "s", "r_point", "hashed_to_curve_r", "status"))
+                line["checks"]["bit_exact_vs_oracle_first_%d" % sample] = bool(same)
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

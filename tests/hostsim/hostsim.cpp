@@ -93,8 +93,9 @@ void hs_sha256(const uint8_t* p, uint32_t n, uint8_t* out) {
 void hs_vb_mul(const uint8_t* p64, const uint8_t* k32, uint8_t* out64) {
     aff p; ld_point_be(p, p64);
     sc k = ld_sc_be(k32);
-    uint32_t tab[VB_TAB_WORDS];
-    jac r = vb_mul_point(p, k, tab, 1);
+    uint32_t tabw[VB_TAB_WORDS];
+    vb_tab_linear tab{tabw};
+    jac r = vb_mul_point(p, k, tab);
     aff q = r.inf ? aff_infinity() : aff_from_jac_zinv(r, fe_inv(r.z));
     st_point_be(out64, q);
 }
@@ -114,13 +115,17 @@ int hs_sign_batch(int version, uint32_t n, const uint8_t* msgs, const uint64_t* 
     sign_args a;
     a.version = version; a.n = n; a.msgs.base = msgs; a.msgs.offs = offs; a.msgs.fixed_len = msg_len;
     a.sk = sk; a.r = r; a.pk = pk; a.nullifier = nul; a.c = c; a.s = s; a.r_point = r_point; a.hashed_to_curve_r = hr;
-    a.status = status; a.ws = ws.data(); a.gtab = g_tab.data(); a.gw = gw;
-    uint32_t tab[VB_TAB_WORDS];
+    a.status = status; a.ws = ws.data(); a.gtab = g_tab.data(); a.gw = gw; a.vbtab = nullptr;
+    uint32_t tabw[VB_TAB_WORDS * 4];
     for (uint32_t i = 0; i < n; i++) sign_stage_fixed(i, a);
     run_binv(a.ws, n, 2 * n, binv_threads);
     for (uint32_t i = 0; i < n; i++) sign_stage_h2c(i, a);
     run_binv(a.ws, n, n, binv_threads);
-    for (uint32_t i = 0; i < n; i++) sign_stage_varbase(i, a, tab, 1);
+    // alternate between the two table layouts the kernels can use
+    for (uint32_t i = 0; i < n; i++) {
+        if (i & 1) sign_stage_varbase(i, a, vb_tab_linear{tabw});
+        else sign_stage_varbase(i, a, vb_tab_strided{tabw + (i & 3), 4});
+    }
     run_binv(a.ws, n, 2 * n, binv_threads);
     for (uint32_t i = 0; i < n; i++) sign_stage_final(i, a);
     return 0;
@@ -134,11 +139,14 @@ int hs_verify_batch(int version, uint32_t n, const uint8_t* msgs, const uint64_t
     verify_args a;
     a.version = version; a.n = n; a.msgs.base = msgs; a.msgs.offs = offs; a.msgs.fixed_len = msg_len;
     a.pk = pk; a.nullifier = nul; a.c = c; a.s = s; a.r_point = r_point; a.hashed_to_curve_r = hr;
-    a.ok = ok; a.ws = ws.data(); a.gtab = g_tab.data(); a.gw = gw;
-    uint32_t tab[VB_TAB_WORDS];
+    a.ok = ok; a.ws = ws.data(); a.gtab = g_tab.data(); a.gw = gw; a.vbtab = nullptr;
+    uint32_t tabw[VB_TAB_WORDS * 4];
     for (uint32_t i = 0; i < n; i++) verify_stage_h2c(i, a);
     run_binv(a.ws, n, n, binv_threads);
-    for (uint32_t i = 0; i < n; i++) verify_stage_muls(i, a, tab, 1);
+    for (uint32_t i = 0; i < n; i++) {
+        if (i & 1) verify_stage_muls(i, a, vb_tab_linear{tabw});
+        else verify_stage_muls(i, a, vb_tab_strided{tabw + (i & 3), 4});
+    }
     run_binv(a.ws, n, 2 * n, binv_threads);
     for (uint32_t i = 0; i < n; i++) verify_stage_final(i, a);
     return 0;

@@ -24,6 +24,7 @@ struct PendingCopy { void* dst; const void* src; size_t bytes; };
 struct Lane {
     cudaStream_t stream = nullptr;
     uint32_t* ws = nullptr;          // WS_SLOTS * chunk * 32 bytes
+    uint32_t* vbtab = nullptr;       // chunk * 512 bytes of window-table scratch (global-table builds)
     uint8_t* d_io = nullptr;         // device arena for inputs and outputs of one chunk
     size_t d_io_cap = 0, d_io_used = 0;
     uint8_t* h_stage = nullptr;      // pinned staging arena (same layout as d_io)
@@ -248,6 +249,7 @@ void plume_ctx_destroy(plume_ctx* ctx) {
     for (auto& e : ctx->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (Lane& L : ctx->lanes) {
         if (L.ws) cudaFree(L.ws);
+        if (L.vbtab) cudaFree(L.vbtab);
         if (L.d_io) cudaFree(L.d_io);
         if (L.h_stage) cudaFreeHost(L.h_stage);
         if (L.stream) cudaStreamDestroy(L.stream);
@@ -282,6 +284,9 @@ int plume_ctx_create(plume_ctx** out, int device, int fixed_window_bits) {
     for (Lane& L : c->lanes) {
         CU(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
         CU(cudaMalloc(&L.ws, (size_t)WS_SLOTS * c->chunk * 32));
+#ifdef PLUME_VB_TAB_GLOBAL
+        CU(cudaMalloc(&L.vbtab, c->chunk * (size_t)VB_TAB_WORDS * 4));
+#endif
     }
     // generator table: entries -> batched inversion -> affine
     const int nwin = (256 + w - 1) / w;
@@ -361,6 +366,25 @@ int plume_measure_imad_peak(plume_ctx* ctx, int iters, double* lp_per_s) {
     return PLUME_OK;
 }
 
+int plume_debug_fe_op(plume_ctx* ctx, int op, size_t n, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    if (!ctx || !a || !b || !out) return PLUME_E_ARG;
+    if (n == 0) return PLUME_OK;
+    ScopedDevice sd(ctx->device);
+    uint32_t *da = nullptr, *db = nullptr, *dout = nullptr;
+    cudaStream_t s = ctx->lanes[0].stream;
+    CU(cudaMalloc(&da, n * 32));
+    CU(cudaMalloc(&db, n * 32));
+    CU(cudaMalloc(&dout, n * 32));
+    CU(cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(db, b, n * 32, cudaMemcpyHostToDevice, s));
+    CU(launch_debug_fe_op(op, (uint32_t)n, da, db, dout, s));
+    ctx->launches++;
+    CU(cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    cudaFree(da); cudaFree(db); cudaFree(dout);
+    return PLUME_OK;
+}
+
 // ---- device-pointer variants ---------------------------------------------------------------------------------
 int plume_sign_batch_device(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets,
                             size_t msg_len, const uint8_t* sk, const uint8_t* r, uint8_t* pk, uint8_t* nullifier,
@@ -377,7 +401,7 @@ int plume_sign_batch_device(plume_ctx* ctx, int version, size_t n, const uint8_t
     a.msgs.base = msgs; a.msgs.offs = msg_offsets; a.msgs.fixed_len = (uint32_t)msg_len;
     a.sk = sk; a.r = r; a.pk = pk; a.nullifier = nullifier; a.c = c; a.s = s_out;
     a.r_point = r_point; a.hashed_to_curve_r = hashed_to_curve_r; a.status = status;
-    a.ws = ctx->lanes[0].ws; a.gtab = ctx->gtab; a.gw = ctx->gw;
+    a.ws = ctx->lanes[0].ws; a.gtab = ctx->gtab; a.gw = ctx->gw; a.vbtab = ctx->lanes[0].vbtab;
     return enqueue_sign(ctx, a, (cudaStream_t)stream);
 }
 
@@ -396,7 +420,7 @@ int plume_verify_batch_device(plume_ctx* ctx, int version, size_t n, const uint8
     a.version = version; a.n = (uint32_t)n;
     a.msgs.base = msgs; a.msgs.offs = msg_offsets; a.msgs.fixed_len = (uint32_t)msg_len;
     a.pk = pk; a.nullifier = nullifier; a.c = c; a.s = s_in; a.r_point = r_point; a.hashed_to_curve_r = hashed_to_curve_r;
-    a.ok = ok; a.ws = ctx->lanes[0].ws; a.gtab = ctx->gtab; a.gw = ctx->gw;
+    a.ok = ok; a.ws = ctx->lanes[0].ws; a.gtab = ctx->gtab; a.gw = ctx->gw; a.vbtab = ctx->lanes[0].vbtab;
     return enqueue_verify(ctx, a, (cudaStream_t)stream);
 }
 
@@ -446,7 +470,7 @@ int plume_sign_batch(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs,
         a.r_point = r_point ? lane_output(L, cn * 64, &o_rp) : nullptr;
         a.hashed_to_curve_r = hashed_to_curve_r ? lane_output(L, cn * 64, &o_hr) : nullptr;
         a.status = lane_output(L, cn, &o_st);
-        a.ws = L.ws; a.gtab = ctx->gtab; a.gw = ctx->gw;
+        a.ws = L.ws; a.gtab = ctx->gtab; a.gw = ctx->gw; a.vbtab = L.vbtab;
         if (int rc = enqueue_sign(ctx, a, L.stream)) return rc;
         if (int rc = lane_fetch(ctx, L, pk + i0 * 64, o_pk, cn * 64)) return rc;
         if (int rc = lane_fetch(ctx, L, nullifier + i0 * 64, o_nul, cn * 64)) return rc;
@@ -492,7 +516,7 @@ int plume_verify_batch(plume_ctx* ctx, int version, size_t n, const uint8_t* msg
         a.pk = d_pk; a.nullifier = d_nul; a.c = d_c; a.s = d_s; a.r_point = d_rp; a.hashed_to_curve_r = d_hr;
         size_t o_ok;
         a.ok = lane_output(L, cn, &o_ok);
-        a.ws = L.ws; a.gtab = ctx->gtab; a.gw = ctx->gw;
+        a.ws = L.ws; a.gtab = ctx->gtab; a.gw = ctx->gw; a.vbtab = L.vbtab;
         if (int rc = enqueue_verify(ctx, a, L.stream)) return rc;
         if (int rc = lane_fetch(ctx, L, ok + i0, o_ok, cn)) return rc;
     }

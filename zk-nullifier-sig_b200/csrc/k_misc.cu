@@ -25,6 +25,28 @@ __global__ void __launch_bounds__(128) k_gtab_norm(uint32_t ne, uint32_t* tab, c
     if (e < ne) gtab_norm_body(e, tab, zs);
 }
 
+// element-wise field operation on raw little-endian limb arrays (test hook: plume_debug_fe_op)
+__global__ void __launch_bounds__(128) k_debug_fe_op(int op, uint32_t n, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe x = ld_fe(a + (size_t)i * 8), y = ld_fe(b + (size_t)i * 8), r;
+    switch (op) {
+        case 0: r = fe_mul(x, y); break;
+        case 1: r = fe_sqr(x); break;
+        case 2: r = fe_add(x, y); break;
+        case 3: r = fe_sub(x, y); break;
+        case 4: r = fe_inv(x); break;
+        case 5: r = fe_norm(x); break;
+        case 6: r = fe_mul_small(x, y.v[0]); break;
+        case 7: r = fe_pow_pm3d4(x); break;
+        case 8: r = fe_neg(x); break;
+        case 9: r = fe_sqrt_cand(x); break;
+        case 10: r = fe_set_u32(fe_is_zero(x) ? 1u : 0u); break;
+        default: r = fe_zero();
+    }
+    st_fe(out + (size_t)i * 8, r);
+}
+
 // 8 independent 64-bit accumulators per thread, each fed by mad.wide.u32 (IMAD.WIDE.U32):
 // iters * 8 * 8 multiply-adds per thread, no memory traffic inside the loop.
 __global__ void k_imad_peak(uint32_t* sink, int iters) {
@@ -75,6 +97,10 @@ cudaError_t launch_gtab_entries(uint32_t ne, uint32_t* tab, uint32_t* zs, const 
 }
 cudaError_t launch_gtab_norm(uint32_t ne, uint32_t* tab, const uint32_t* zs, cudaStream_t s) {
     k_gtab_norm<<<grid_for(ne, 128), 128, 0, s>>>(ne, tab, zs);
+    return cudaGetLastError();
+}
+cudaError_t launch_debug_fe_op(int op, uint32_t n, const uint32_t* a, const uint32_t* b, uint32_t* out, cudaStream_t s) {
+    k_debug_fe_op<<<grid_for(n, 128), 128, 0, s>>>(op, n, a, b, out);
     return cudaGetLastError();
 }
 cudaError_t launch_imad_peak(uint32_t* sink, int iters, int blocks, int threads, cudaStream_t s) {

@@ -9,10 +9,10 @@ __global__ void __launch_bounds__(128) k_sign_h2c(sign_args a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.n) sign_stage_h2c(i, a);
 }
-__global__ void __launch_bounds__(VB_BLOCK) k_sign_varbase(sign_args a) {
+__global__ void __launch_bounds__(VB_BLOCK, PLUME_VB_MINBLOCKS) k_sign_varbase(sign_args a) {
     extern __shared__ uint32_t vb_smem[];
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < a.n) sign_stage_varbase(i, a, vb_smem + threadIdx.x, VB_BLOCK);
+    if (i < a.n) sign_stage_varbase(i, a, VB_TAB(a, i));
 }
 __global__ void __launch_bounds__(128) k_sign_final(sign_args a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -38,5 +38,6 @@ cudaError_t launch_sign_final(const sign_args& a, cudaStream_t s) {
     return cudaGetLastError();
 }
 cudaError_t kernels_init_sign() {
+    if (VB_SMEM_BYTES == 0) return cudaSuccess;
     return cudaFuncSetAttribute(k_sign_varbase, cudaFuncAttributeMaxDynamicSharedMemorySize, VB_SMEM_BYTES);
 }

@@ -5,10 +5,10 @@ __global__ void __launch_bounds__(128) k_verify_h2c(verify_args a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.n) verify_stage_h2c(i, a);
 }
-__global__ void __launch_bounds__(VB_BLOCK) k_verify_muls(verify_args a) {
+__global__ void __launch_bounds__(VB_BLOCK, PLUME_VB_MINBLOCKS) k_verify_muls(verify_args a) {
     extern __shared__ uint32_t vb_smem[];
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < a.n) verify_stage_muls(i, a, vb_smem + threadIdx.x, VB_BLOCK);
+    if (i < a.n) verify_stage_muls(i, a, VB_TAB(a, i));
 }
 __global__ void __launch_bounds__(128) k_verify_final(verify_args a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -30,5 +30,6 @@ cudaError_t launch_verify_final(const verify_args& a, cudaStream_t s) {
     return cudaGetLastError();
 }
 cudaError_t kernels_init_verify() {
+    if (VB_SMEM_BYTES == 0) return cudaSuccess;
     return cudaFuncSetAttribute(k_verify_muls, cudaFuncAttributeMaxDynamicSharedMemorySize, VB_SMEM_BYTES);
 }

@@ -5,9 +5,23 @@
 #include <cuda_runtime.h>
 #include "stages.cuh"
 
-// threads per block of the kernels that keep a per-thread table in shared memory
-#define VB_BLOCK 128
+// Variable-base kernels: threads per block, minimum resident blocks per SM (register cap), and where
+// the per-thread window table lives -- shared memory (default) or a global scratch array
+// (-DPLUME_VB_TAB_GLOBAL: no shared memory, occupancy limited by registers only).
+#ifndef PLUME_VB_BLOCK
+#define PLUME_VB_BLOCK 128
+#endif
+#ifndef PLUME_VB_MINBLOCKS
+#define PLUME_VB_MINBLOCKS 1
+#endif
+#define VB_BLOCK PLUME_VB_BLOCK
+#ifdef PLUME_VB_TAB_GLOBAL
+#define VB_SMEM_BYTES 0
+#define VB_TAB(a, i) vb_tab_linear{(a).vbtab + (size_t)(i) * VB_TAB_WORDS}
+#else
 #define VB_SMEM_BYTES (VB_TAB_WORDS * 4 * VB_BLOCK)
+#define VB_TAB(a, i) vb_tab_strided{vb_smem + threadIdx.x, VB_BLOCK}
+#endif
 
 cudaError_t launch_sign_fixed(const sign_args& a, cudaStream_t s);
 cudaError_t launch_sign_h2c(const sign_args& a, cudaStream_t s);
@@ -26,4 +40,5 @@ cudaError_t launch_gtab_entries(uint32_t ne, uint32_t* tab, uint32_t* zs, const 
 cudaError_t launch_gtab_norm(uint32_t ne, uint32_t* tab, const uint32_t* zs, cudaStream_t s);
 // integer-pipe microbenchmark: every thread runs `iters` * 64 independent-chain IMAD.WIDE.U32
 cudaError_t launch_imad_peak(uint32_t* sink, int iters, int blocks, int threads, cudaStream_t s);
+cudaError_t launch_debug_fe_op(int op, uint32_t n, const uint32_t* a, const uint32_t* b, uint32_t* out, cudaStream_t s);
 cudaError_t kernels_init();  // opt-in shared memory sizes

@@ -53,30 +53,63 @@ PLUME_DEV jac fb_mul(const sc& k, const uint32_t* gtab, int w) {
 // ---------------------------------------------------------------------------------------------
 #define VB_TAB_WORDS 128
 
-PLUME_DEV void vb_tab_store(uint32_t* tab, int stride, int e, const fe& x, const fe& y) {
+// Where a thread's table lives.  vb_tab_strided: word (e, i) at p[(e*16 + i) * stride] -- shared memory,
+// p already offset by the thread index and stride = threads per block, so every access is
+// bank-conflict free whatever entries the lanes pick.  vb_tab_linear: 128 contiguous words per
+// thread in global memory (L1/L2 resident scratch), entry = 64 contiguous bytes = four 128-bit loads.
+struct vb_tab_strided {
+    uint32_t* p;
+    int stride;
+    PLUME_DEV_MEMBER void store(int e, const fe& x, const fe& y) const {
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        tab[(e * 16 + i) * stride] = x.v[i];
-        tab[(e * 16 + 8 + i) * stride] = y.v[i];
+        for (int i = 0; i < 8; i++) {
+            p[(e * 16 + i) * stride] = x.v[i];
+            p[(e * 16 + 8 + i) * stride] = y.v[i];
+        }
     }
-}
-PLUME_DEV void vb_tab_load(const uint32_t* tab, int stride, int e, fe& x, fe& y) {
+    PLUME_DEV_MEMBER void load(int e, fe& x, fe& y) const {
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        x.v[i] = tab[(e * 16 + i) * stride];
-        y.v[i] = tab[(e * 16 + 8 + i) * stride];
+        for (int i = 0; i < 8; i++) {
+            x.v[i] = p[(e * 16 + i) * stride];
+            y.v[i] = p[(e * 16 + 8 + i) * stride];
+        }
     }
-}
+};
+struct vb_tab_linear {
+    uint32_t* p;
+    PLUME_DEV_MEMBER void store(int e, const fe& x, const fe& y) const {
+#ifdef PLUME_HOSTSIM
+        for (int i = 0; i < 8; i++) { p[e * 16 + i] = x.v[i]; p[e * 16 + 8 + i] = y.v[i]; }
+#else
+        uint4* q = reinterpret_cast<uint4*>(p + e * 16);
+        q[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+        q[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+        q[2] = make_uint4(y.v[0], y.v[1], y.v[2], y.v[3]);
+        q[3] = make_uint4(y.v[4], y.v[5], y.v[6], y.v[7]);
+#endif
+    }
+    PLUME_DEV_MEMBER void load(int e, fe& x, fe& y) const {
+#ifdef PLUME_HOSTSIM
+        for (int i = 0; i < 8; i++) { x.v[i] = p[e * 16 + i]; y.v[i] = p[e * 16 + 8 + i]; }
+#else
+        const uint4* q = reinterpret_cast<const uint4*>(p + e * 16);
+        uint4 a = q[0], b = q[1], c = q[2], d = q[3];
+        x.v[0] = a.x; x.v[1] = a.y; x.v[2] = a.z; x.v[3] = a.w; x.v[4] = b.x; x.v[5] = b.y; x.v[6] = b.z; x.v[7] = b.w;
+        y.v[0] = c.x; y.v[1] = c.y; y.v[2] = c.z; y.v[3] = c.w; y.v[4] = d.x; y.v[5] = d.y; y.v[6] = d.z; y.v[7] = d.w;
+#endif
+    }
+};
 
 // builds the table for the affine, on-curve, non-identity point (px, py); returns Zg
-PLUME_DEV fe vb_build_table(const fe& px, const fe& py, uint32_t* tab, int stride) {
+template <class Tab>
+PLUME_DEV fe vb_build_table(const fe& px, const fe& py, const Tab& tab) {
     fe hs[8];  // hs[k] = Z_{k+1} / Z_k, k = 1..7 (local memory; touched 14 times per table)
     jac cur;
     cur.x = px; cur.y = py; cur.z = fe_one(); cur.inf = 0;
-    vb_tab_store(tab, stride, 0, px, py);
+    tab.store(0, px, py);
     cur = jac_dbl(cur);
     hs[1] = cur.z;
-    vb_tab_store(tab, stride, 1, cur.x, cur.y);
+    tab.store(1, cur.x, cur.y);
 #pragma unroll 1
     for (int k = 2; k < 8; k++) {
         // cur = k*P (Jacobian) ; next = cur + P ; Z_next = Z_cur * H with H = px*Z^2 - X
@@ -84,7 +117,7 @@ PLUME_DEV fe vb_build_table(const fe& px, const fe& py, uint32_t* tab, int strid
         fe H = fe_sub(fe_mul(px, z2), cur.x);
         cur = jac_add_aff(cur, px, py, 0);
         hs[k] = H;
-        vb_tab_store(tab, stride, k, cur.x, cur.y);
+        tab.store(k, cur.x, cur.y);
     }
     fe zg = cur.z;
     fe ratio = fe_one();
@@ -92,22 +125,23 @@ PLUME_DEV fe vb_build_table(const fe& px, const fe& py, uint32_t* tab, int strid
     for (int k = 7; k >= 1; k--) {
         ratio = fe_mul(ratio, hs[k]);  // Z_8 / Z_k
         fe x, y;
-        vb_tab_load(tab, stride, k - 1, x, y);
+        tab.load(k - 1, x, y);
         fe r2 = fe_sqr(ratio);
         x = fe_mul(x, r2);
         y = fe_mul(y, fe_mul(r2, ratio));
-        vb_tab_store(tab, stride, k - 1, x, y);
+        tab.store(k - 1, x, y);
     }
     return zg;
 }
 
 // acc += d * T  (d in [-8, 8], `flip` negates, `endo` applies (x, y) -> (beta*x, y))
-PLUME_DEV jac vb_add_digit(const jac& acc, int d, uint32_t flip, bool endo, const uint32_t* tab, int stride) {
+template <class Tab>
+PLUME_DEV jac vb_add_digit(const jac& acc, int d, uint32_t flip, bool endo, const Tab& tab) {
     if (d == 0) return acc;
     uint32_t neg = (d < 0 ? 1u : 0u) ^ flip;
     int e = (d < 0 ? -d : d) - 1;
     fe x, y;
-    vb_tab_load(tab, stride, e, x, y);
+    tab.load(e, x, y);
     if (endo) x = fe_mul(x, ec_beta());
     fe ny = fe_neg(y);
     y = fe_cmov(y, ny, neg != 0);
@@ -115,7 +149,8 @@ PLUME_DEV jac vb_add_digit(const jac& acc, int d, uint32_t flip, bool endo, cons
 }
 
 // k * P from the prepared table; k canonical in [0, n)
-PLUME_DEV jac vb_mul_tab(const sc& k, const uint32_t* tab, int stride, const fe& zg) {
+template <class Tab>
+PLUME_DEV jac vb_mul_tab(const sc& k, const Tab& tab, const fe& zg) {
     glv_half h1, h2;
     glv_split(k, h1, h2);
     booth_reg b1 = booth_init(h1), b2 = booth_init(h2);
@@ -126,8 +161,9 @@ PLUME_DEV jac vb_mul_tab(const sc& k, const uint32_t* tab, int stride, const fe&
         for (int j = 0; j < 4; j++) acc = jac_dbl(acc);
         int d1 = booth_next(b1);
         int d2 = booth_next(b2);
-        acc = vb_add_digit(acc, d1, h1.neg, false, tab, stride);
-        acc = vb_add_digit(acc, d2, h2.neg, true, tab, stride);
+        // one addition body for both halves (the loop is kept rolled on purpose: code size)
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) acc = vb_add_digit(acc, h ? d2 : d1, h ? h2.neg : h1.neg, h != 0, tab);
     }
     if (!acc.inf) acc.z = fe_mul(acc.z, zg);
     return acc;

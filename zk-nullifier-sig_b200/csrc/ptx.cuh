@@ -13,6 +13,7 @@
 #ifdef PLUME_HOSTSIM
 #define PLUME_DEV static inline
 #define PLUME_DEV_NOINLINE static
+#define PLUME_DEV_MEMBER inline
 static thread_local uint32_t plume_cc_ = 0;
 PLUME_DEV uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; plume_cc_ = (uint32_t)(t >> 32); return (uint32_t)t; }
 PLUME_DEV uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + plume_cc_; plume_cc_ = (uint32_t)(t >> 32); return (uint32_t)t; }
@@ -31,7 +32,8 @@ PLUME_DEV uint32_t bswap32(uint32_t x) { return __builtin_bswap32(x); }
 PLUME_DEV uint32_t rotr32(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
 #else
 #define PLUME_DEV __device__ __forceinline__
-#define PLUME_DEV_NOINLINE __device__ __noinline__
+#define PLUME_DEV_NOINLINE static __device__ __noinline__
+#define PLUME_DEV_MEMBER __device__ __forceinline__
 PLUME_DEV uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 PLUME_DEV uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 PLUME_DEV uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }

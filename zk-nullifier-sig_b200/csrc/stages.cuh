@@ -212,6 +212,7 @@ struct sign_args {
     uint32_t* ws;
     const uint32_t* gtab;
     int gw;
+    uint32_t* vbtab;      // n x 128 words of table scratch (global-table builds only)
 };
 
 PLUME_DEV sc sc_one() { sc r; for (int i = 0; i < 8; i++) r.v[i] = (i == 0); return r; }
@@ -265,8 +266,9 @@ PLUME_DEV void sign_stage_h2c(uint32_t i, const sign_args& a) {
     ws_store_jac(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i, h);
 }
 
-// tab: this thread's table (stride = distance in words between consecutive table words)
-PLUME_DEV void sign_stage_varbase(uint32_t i, const sign_args& a, uint32_t* tab, int stride) {
+// tab: this thread's table storage (vb_tab_strided in shared memory or vb_tab_linear in global scratch)
+template <class Tab>
+PLUME_DEV void sign_stage_varbase(uint32_t i, const sign_args& a, const Tab& tab) {
     aff h = ws_load_affine(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i);
     ws_store_aff(a.ws, a.n, WS_HX, WS_HY, i, h);
     if (h.inf) {
@@ -277,14 +279,14 @@ PLUME_DEV void sign_stage_varbase(uint32_t i, const sign_args& a, uint32_t* tab,
         ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, o);
         return;
     }
-    fe zg = vb_build_table(h.x, h.y, tab, stride);
+    fe zg = vb_build_table(h.x, h.y, tab);
     sc r = ld_sc_be(a.r + (size_t)i * 32);
     sc sk = ld_sc_be(a.sk + (size_t)i * 32);
     if (!sc_is_valid_nonzero(sk)) sk = sc_one();
     if (!sc_is_valid_nonzero(r)) r = sc_one();
 #pragma unroll 1
     for (int which = 0; which < 2; which++) {
-        jac o = vb_mul_tab(which == 0 ? r : sk, tab, stride, zg);
+        jac o = vb_mul_tab(which == 0 ? r : sk, tab, zg);
         if (which == 0) ws_store_jac(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i, o);
         else ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, o);
     }
@@ -362,6 +364,7 @@ struct verify_args {
     uint32_t* ws;
     const uint32_t* gtab;
     int gw;
+    uint32_t* vbtab;
 };
 
 // ok[i] is used as scratch between stages: 1 = inputs well-formed so far, 0 = reject
@@ -387,13 +390,15 @@ PLUME_DEV void verify_stage_h2c(uint32_t i, const verify_args& a) {
 }
 
 // k * P for an affine P that may be the identity
-PLUME_DEV jac vb_mul_point(const aff& p, const sc& k, uint32_t* tab, int stride) {
+template <class Tab>
+PLUME_DEV jac vb_mul_point(const aff& p, const sc& k, const Tab& tab) {
     if (p.inf) return jac_infinity();
-    fe zg = vb_build_table(p.x, p.y, tab, stride);
-    return vb_mul_tab(k, tab, stride, zg);
+    fe zg = vb_build_table(p.x, p.y, tab);
+    return vb_mul_tab(k, tab, zg);
 }
 
-PLUME_DEV void verify_stage_muls(uint32_t i, const verify_args& a, uint32_t* tab, int stride) {
+template <class Tab>
+PLUME_DEV void verify_stage_muls(uint32_t i, const verify_args& a, const Tab& tab) {
     aff h = ws_load_affine(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i);
     ws_store_aff(a.ws, a.n, WS_HX, WS_HY, i, h);
     // remember whether h is the identity: WS_RX limb 0
@@ -413,11 +418,11 @@ PLUME_DEV void verify_stage_muls(uint32_t i, const verify_args& a, uint32_t* tab
     sc mc = sc_neg(c);
     // A = G*s - pk*c   (lib.rs:101)
     jac A = fb_mul(s, a.gtab, a.gw);
-    A = jac_add(A, vb_mul_point(pk, mc, tab, stride));
+    A = jac_add(A, vb_mul_point(pk, mc, tab));
     ws_store_jac(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i, A);
     // B = h*s - nul*c  (lib.rs:109)
-    jac B = vb_mul_point(h, s, tab, stride);
-    B = jac_add(B, vb_mul_point(nul, mc, tab, stride));
+    jac B = vb_mul_point(h, s, tab);
+    B = jac_add(B, vb_mul_point(nul, mc, tab));
     ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, B);
 }
 

@@ -4,7 +4,7 @@ import ctypes
 import os
 
 PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(PKG, "libplume_b200.so")
+LIB_PATH = os.environ.get("PLUME_B200_LIB") or os.path.join(PKG, "libplume_b200.so")   # env: experiment builds
 
 _u8p = ctypes.c_void_p
 _lib = None
@@ -29,6 +29,7 @@ SYMBOLS = {
     "plume_ctx_launch_count": (ctypes.c_uint64, [ctypes.c_void_p]),
     "plume_ctx_set_profiling": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "plume_ctx_stage_ms": (ctypes.c_double, [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint64)]),
+    "plume_debug_fe_op": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, _u8p, _u8p, _u8p]),
     "plume_measure_imad_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
 }
 

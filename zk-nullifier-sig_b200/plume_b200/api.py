@@ -107,6 +107,13 @@ class PlumeContext:
         self._check(self._lib.plume_measure_imad_peak(self._h, iters, ctypes.byref(v)), "plume_measure_imad_peak")
         return v.value
 
+    def debug_fe_op(self, op, a, b):
+        """plume_debug_fe_op on u32[n,8] little-endian limb arrays."""
+        a = np.ascontiguousarray(a, dtype=np.uint32); b = np.ascontiguousarray(b, dtype=np.uint32)
+        out = np.empty_like(a)
+        self._check(self._lib.plume_debug_fe_op(self._h, op, a.shape[0], _ptr(a), _ptr(b), _ptr(out)), "plume_debug_fe_op")
+        return out
+
     # ---- batch entry points on host (numpy) buffers ---------------------------------------------------
     @staticmethod
     def _msgs(msgs, msg_len):
@@ -150,6 +157,50 @@ class PlumeContext:
                                           _ptr(c), _ptr(s), _ptr(rp), _ptr(hr), _ptr(ok))
         self._check(rc, "plume_verify_batch")
         return ok
+
+    # ---- device-pointer entry points (raw addresses, e.g. torch tensors' data_ptr()) -----------------
+    def sign_batch_device(self, version, n, msgs, msg_offsets, msg_len, sk, r, pk, nullifier, c, s,
+                          r_point, hashed_to_curve_r, status, stream=0):
+        vp = ctypes.c_void_p
+        rc = self._lib.plume_sign_batch_device(self._h, version, n, vp(msgs), vp(msg_offsets or None), msg_len, vp(sk), vp(r),
+                                               vp(pk), vp(nullifier), vp(c), vp(s), vp(r_point or None),
+                                               vp(hashed_to_curve_r or None), vp(status), vp(stream or None))
+        self._check(rc, "plume_sign_batch_device")
+
+    def verify_batch_device(self, version, n, msgs, msg_offsets, msg_len, pk, nullifier, c, s, r_point,
+                            hashed_to_curve_r, ok, stream=0):
+        vp = ctypes.c_void_p
+        rc = self._lib.plume_verify_batch_device(self._h, version, n, vp(msgs), vp(msg_offsets or None), msg_len, vp(pk),
+                                                 vp(nullifier), vp(c), vp(s), vp(r_point or None),
+                                                 vp(hashed_to_curve_r or None), vp(ok), vp(stream or None))
+        self._check(rc, "plume_verify_batch_device")
+
+    def hash_to_curve_batch_device(self, n, msgs, msg_offsets, msg_len, out, stream=0):
+        vp = ctypes.c_void_p
+        rc = self._lib.plume_hash_to_curve_batch_device(self._h, n, vp(msgs), vp(msg_offsets or None), msg_len, vp(out),
+                                                        vp(stream or None))
+        self._check(rc, "plume_hash_to_curve_batch_device")
+
+    # raw host addresses (e.g. pinned torch tensors): same C entry points as sign_batch / verify_batch
+    def sign_batch_ptr(self, version, n, msgs, msg_offsets, msg_len, sk, r, pk, nullifier, c, s, r_point,
+                       hashed_to_curve_r, status):
+        vp = ctypes.c_void_p
+        rc = self._lib.plume_sign_batch(self._h, version, n, vp(msgs), vp(msg_offsets or None), msg_len, vp(sk), vp(r), vp(pk),
+                                        vp(nullifier), vp(c), vp(s), vp(r_point or None), vp(hashed_to_curve_r or None),
+                                        vp(status))
+        self._check(rc, "plume_sign_batch")
+
+    def verify_batch_ptr(self, version, n, msgs, msg_offsets, msg_len, pk, nullifier, c, s, r_point, hashed_to_curve_r, ok):
+        vp = ctypes.c_void_p
+        rc = self._lib.plume_verify_batch(self._h, version, n, vp(msgs), vp(msg_offsets or None), msg_len, vp(pk),
+                                          vp(nullifier), vp(c), vp(s), vp(r_point or None), vp(hashed_to_curve_r or None),
+                                          vp(ok))
+        self._check(rc, "plume_verify_batch")
+
+    def hash_to_curve_batch_ptr(self, n, msgs, msg_offsets, msg_len, out):
+        vp = ctypes.c_void_p
+        rc = self._lib.plume_hash_to_curve_batch(self._h, n, vp(msgs), vp(msg_offsets or None), msg_len, vp(out))
+        self._check(rc, "plume_hash_to_curve_batch")
 
     def hash_to_curve_batch(self, msgs, out=None):
         blob, offs, mlen, n = self._msgs(msgs, None)

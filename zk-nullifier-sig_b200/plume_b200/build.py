@@ -39,10 +39,17 @@ def _stale(target, sources):
     return any(os.path.getmtime(s) > t for s in sources)
 
 
-def build(force=False, verbose=True):
+def build(force=False, verbose=True, variant=None, defines=()):
+    """variant/defines: build an experiment library libplume_b200_<variant>.so with extra -D flags
+    (selected at run time with PLUME_B200_LIB=<path>); the default build is the shipped library."""
+    global BUILD, LIB
+    if variant:
+        BUILD = os.path.join(PKG, "build", variant)
+        LIB = os.path.join(PKG, "libplume_b200_%s.so" % variant)
     os.makedirs(BUILD, exist_ok=True)
     nvcc = _nvcc()
     deps = _deps()
+    flags = NVCC_FLAGS + ["-D" + d for d in defines]
 
     def compile_unit(u):
         src, obj = os.path.join(CSRC, u + ".cu"), os.path.join(BUILD, u + ".o")
@@ -50,7 +57,7 @@ def build(force=False, verbose=True):
             return u, False
         log = os.path.join(BUILD, u + ".log")
         with open(log, "w") as lf:
-            r = subprocess.run([nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj], stdout=lf, stderr=subprocess.STDOUT)
+            r = subprocess.run([nvcc] + flags + ["-c", src, "-o", obj], stdout=lf, stderr=subprocess.STDOUT)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s" % (u, open(log).read()[-4000:]))
         return u, True
@@ -69,4 +76,8 @@ def build(force=False, verbose=True):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv)
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    if args:   # build.py <variant> DEF1 DEF2=val ...
+        build(force="--force" in sys.argv, variant=args[0], defines=args[1:])
+    else:
+        build(force="--force" in sys.argv)
