@@ -143,10 +143,7 @@ int hs_verify_batch(int version, uint32_t n, const uint8_t* msgs, const uint64_t
     uint32_t tabw[VB_TAB_WORDS * 4];
     for (uint32_t i = 0; i < n; i++) verify_stage_h2c(i, a);
     run_binv(a.ws, n, n, binv_threads);
-    for (uint32_t i = 0; i < n; i++) {
-        if (i & 1) verify_stage_muls(i, a, vb_tab_linear{tabw});
-        else verify_stage_muls(i, a, vb_tab_strided{tabw + (i & 3), 4});
-    }
+    for (uint32_t i = 0; i < n; i++) verify_stage_muls(i, a, vb_tab_linear{tabw}, vb_tab_linear{tabw + VB_TAB_WORDS});
     run_binv(a.ws, n, 2 * n, binv_threads);
     for (uint32_t i = 0; i < n; i++) verify_stage_final(i, a);
     return 0;

@@ -24,7 +24,7 @@ struct PendingCopy { void* dst; const void* src; size_t bytes; };
 struct Lane {
     cudaStream_t stream = nullptr;
     uint32_t* ws = nullptr;          // WS_SLOTS * chunk * 32 bytes
-    uint32_t* vbtab = nullptr;       // chunk * 512 bytes of window-table scratch (global-table builds)
+    uint32_t* vbtab = nullptr;       // chunk * 1 KiB of window-table scratch in HBM/L2 (verify: two tables per item)
     uint8_t* d_io = nullptr;         // device arena for inputs and outputs of one chunk
     size_t d_io_cap = 0, d_io_used = 0;
     uint8_t* h_stage = nullptr;      // pinned staging arena (same layout as d_io)
@@ -267,7 +267,7 @@ int plume_ctx_create(plume_ctx** out, int device, int fixed_window_bits) {
     if (e != cudaSuccess || ndev == 0)
         return fail(nullptr, PLUME_E_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
     if (device < 0 || device >= ndev) return fail(nullptr, PLUME_E_NO_DEVICE, "device ordinal out of range");
-    int w = fixed_window_bits ? fixed_window_bits : (int)env_size("PLUME_FIXED_WINDOW", 12);
+    int w = fixed_window_bits ? fixed_window_bits : (int)env_size("PLUME_FIXED_WINDOW", 16);
     if (w < 4 || w > 16) return fail(nullptr, PLUME_E_ARG, "fixed_window_bits must be in 4..16");
     ScopedDevice sd(device);
     cudaDeviceProp prop;
@@ -284,9 +284,7 @@ int plume_ctx_create(plume_ctx** out, int device, int fixed_window_bits) {
     for (Lane& L : c->lanes) {
         CU(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
         CU(cudaMalloc(&L.ws, (size_t)WS_SLOTS * c->chunk * 32));
-#ifdef PLUME_VB_TAB_GLOBAL
-        CU(cudaMalloc(&L.vbtab, c->chunk * (size_t)VB_TAB_WORDS * 4));
-#endif
+        CU(cudaMalloc(&L.vbtab, c->chunk * (size_t)VB_TAB_WORDS * 4 * 2));  // two window tables per item (verify)
     }
     // generator table: entries -> batched inversion -> affine
     const int nwin = (256 + w - 1) / w;

@@ -156,36 +156,49 @@ PLUME_DEV fe fe_sub(const fe& a, const fe& b) {
     return r;
 }
 
-// acc[0..7] += (a0, a1, a2, a3) * b as four chained 64-bit lanes.  fe_row4 drops the carry out of
-// the last lane (used where that lane is known not to overflow), fe_row4c adds it into acc[8].
-PLUME_DEV void fe_row4(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+// Rows of the schoolbook product: acc += (a0, a1, ..) * b as chained 64-bit lanes (one IMAD.WIDE.U32.X
+// per lane).  Words a row touches for the first time are pure outputs (multiply-add with a zero
+// addend), so no accumulator ever needs a zeroing move:
+//   fe_row4t : lanes 0..2 accumulate, lane 3 = (acc[6] += .., acc[7] fresh); no carry out of a fresh word
+//   fe_row4c : lanes 0..3 accumulate, the carry out is written to the fresh word acc[8]
+//   fe_rowNf : N lanes, the first N-1 accumulate, the last lane is entirely fresh (squaring)
+PLUME_DEV void fe_row4t(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
     asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\tmadc.hi.cc.u32 %1, %8, %12, %1;\n\t"
         "madc.lo.cc.u32 %2, %9, %12, %2;\n\tmadc.hi.cc.u32 %3, %9, %12, %3;\n\t"
         "madc.lo.cc.u32 %4, %10, %12, %4;\n\tmadc.hi.cc.u32 %5, %10, %12, %5;\n\t"
-        "madc.lo.cc.u32 %6, %11, %12, %6;\n\tmadc.hi.u32 %7, %11, %12, %7;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7])
+        "madc.lo.cc.u32 %6, %11, %12, %6;\n\tmadc.hi.u32 %7, %11, %12, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "=r"(acc[7])
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
 }
 PLUME_DEV void fe_row4c(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
     asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\tmadc.hi.cc.u32 %1, %9, %13, %1;\n\t"
         "madc.lo.cc.u32 %2, %10, %13, %2;\n\tmadc.hi.cc.u32 %3, %10, %13, %3;\n\t"
         "madc.lo.cc.u32 %4, %11, %13, %4;\n\tmadc.hi.cc.u32 %5, %11, %13, %5;\n\t"
-        "madc.lo.cc.u32 %6, %12, %13, %6;\n\tmadc.hi.cc.u32 %7, %12, %13, %7;\n\taddc.u32 %8, %8, 0;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\tmadc.hi.cc.u32 %7, %12, %13, %7;\n\taddc.u32 %8, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=r"(acc[8])
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
 }
-// shorter rows for the squaring (1, 2, 3 lanes; the top lane is always fresh, no carry out)
-PLUME_DEV void fe_row1(uint32_t* acc, uint32_t a0, uint32_t b) {
-    asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(acc[0]), "+r"(acc[1]) : "r"(a0), "r"(b));
+PLUME_DEV void fe_row2f(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t b) {
+    asm("mad.lo.cc.u32 %0, %4, %6, %0;\n\tmadc.hi.cc.u32 %1, %4, %6, %1;\n\tmadc.lo.cc.u32 %2, %5, %6, 0;\n\tmadc.hi.u32 %3, %5, %6, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]) : "r"(a0), "r"(a1), "r"(b));
 }
-PLUME_DEV void fe_row2(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t b) {
-    asm("mad.lo.cc.u32 %0, %4, %6, %0;\n\tmadc.hi.cc.u32 %1, %4, %6, %1;\n\tmadc.lo.cc.u32 %2, %5, %6, %2;\n\tmadc.hi.u32 %3, %5, %6, %3;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]) : "r"(a0), "r"(a1), "r"(b));
-}
-PLUME_DEV void fe_row3(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b) {
+PLUME_DEV void fe_row3f(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b) {
     asm("mad.lo.cc.u32 %0, %6, %9, %0;\n\tmadc.hi.cc.u32 %1, %6, %9, %1;\n\tmadc.lo.cc.u32 %2, %7, %9, %2;\n\tmadc.hi.cc.u32 %3, %7, %9, %3;\n\t"
-        "madc.lo.cc.u32 %4, %8, %9, %4;\n\tmadc.hi.u32 %5, %8, %9, %5;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]) : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+        "madc.lo.cc.u32 %4, %8, %9, 0;\n\tmadc.hi.u32 %5, %8, %9, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]) : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+}
+PLUME_DEV void fe_row4f(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+    asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\tmadc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %12, %2;\n\tmadc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %12, %4;\n\tmadc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %12, 0;\n\tmadc.hi.u32 %7, %11, %12, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "=r"(acc[6]), "=r"(acc[7])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+PLUME_DEV void fe_prod(uint32_t* acc, uint32_t a, uint32_t b) {  // plain 64-bit product (IMAD.WIDE.U32, no carry)
+    uint64_t p = (uint64_t)a * b;
+    acc[0] = (uint32_t)p;
+    acc[1] = (uint32_t)(p >> 32);
 }
 
 // t[0..7] = x[0..7] + y[0..7] + cin, returns the carry out (cin, cout in {0,1}); long additions are
@@ -217,29 +230,28 @@ PLUME_DEV uint32_t fe_add8(uint32_t* t, const uint32_t* x, const uint32_t* y) {
 // that every 64-bit product lands on an aligned register pair and each row is one carry chain
 // of four IMAD.WIDE.U32.X; the E rows and the O rows are two independent dependency streams)
 PLUME_DEV void fe_mul_wide(uint32_t* T, const uint32_t* a, const uint32_t* b) {
-    uint32_t E[17], O[17];
-#pragma unroll
-    for (int i = 0; i < 17; i++) { E[i] = 0; O[i] = 0; }
+    uint32_t E[16], O[16];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        uint64_t pe = (uint64_t)a[2 * k] * b[0], po = (uint64_t)a[2 * k + 1] * b[0];
-        E[2 * k] = (uint32_t)pe; E[2 * k + 1] = (uint32_t)(pe >> 32);
-        O[2 * k] = (uint32_t)po; O[2 * k + 1] = (uint32_t)(po >> 32);
+        fe_prod(E + 2 * k, a[2 * k], b[0]);
+        fe_prod(O + 2 * k, a[2 * k + 1], b[0]);
     }
+    E[8] = 0;  // the only word read before a row has written it (row j = 1 accumulates into limbs 2..8)
 #pragma unroll
     for (int j = 1; j < 8; j++) {
         const int se = (j & 1) ? j + 1 : j, ie = (j & 1) ? 1 : 0;  // E chain: start limb / first a index
         const int so = (j & 1) ? j - 1 : j, io = (j & 1) ? 0 : 1;  // O chain (limb index offset by one)
-        // the carry can leave a row's top lane only when that lane already held a product
+        // A row's top lane holds at most the previous row's carry word, so: odd j -> the E row cannot
+        // carry out and its top word is fresh, the O row carries into a fresh word; even j the other way.
         if (j & 1) {
-            fe_row4(E + se, a[ie], a[ie + 2], a[ie + 4], a[ie + 6], b[j]);
+            fe_row4t(E + se, a[ie], a[ie + 2], a[ie + 4], a[ie + 6], b[j]);
             fe_row4c(O + so, a[io], a[io + 2], a[io + 4], a[io + 6], b[j]);
         } else {
             fe_row4c(E + se, a[ie], a[ie + 2], a[ie + 4], a[ie + 6], b[j]);
-            fe_row4(O + so, a[io], a[io + 2], a[io + 4], a[io + 6], b[j]);
+            fe_row4t(O + so, a[io], a[io + 2], a[io + 4], a[io + 6], b[j]);
         }
     }
-    // T = E + (O << 32)
+    // T = E + (O << 32); E has 16 limbs, O has 15 (limbs 0..14)
     T[0] = E[0];
     uint32_t x[8], y[8], t2[8];
 #pragma unroll
@@ -258,23 +270,23 @@ PLUME_DEV void fe_sqr_wide(uint32_t* T, const uint32_t* a) {
     // Row j multiplies a_j by the a_i (i < j) of the right parity; the row's top lane is always
     // untouched so far, so no row carries out.
     uint32_t E[16], O[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) { E[i] = 0; O[i] = 0; }
     // O rows: j=1: i=0 @0 | j=2: i=1 @2 | j=3: i=0,2 @2 | j=4: i=1,3 @4 | j=5: i=0,2,4 @4 | j=6: i=1,3,5 @6 | j=7: i=0,2,4,6 @6
-    fe_row1(O + 0, a[0], a[1]);
-    fe_row1(O + 2, a[1], a[2]);
-    fe_row2(O + 2, a[0], a[2], a[3]);
-    fe_row2(O + 4, a[1], a[3], a[4]);
-    fe_row3(O + 4, a[0], a[2], a[4], a[5]);
-    fe_row3(O + 6, a[1], a[3], a[5], a[6]);
-    fe_row4(O + 6, a[0], a[2], a[4], a[6], a[7]);
+    fe_prod(O + 0, a[0], a[1]);
+    fe_prod(O + 2, a[1], a[2]);
+    fe_row2f(O + 2, a[0], a[2], a[3]);
+    fe_row2f(O + 4, a[1], a[3], a[4]);
+    fe_row3f(O + 4, a[0], a[2], a[4], a[5]);
+    fe_row3f(O + 6, a[1], a[3], a[5], a[6]);
+    fe_row4f(O + 6, a[0], a[2], a[4], a[6], a[7]);
+    O[14] = 0;
     // E rows: j=2: i=0 @2 | j=3: i=1 @4 | j=4: i=0,2 @4 | j=5: i=1,3 @6 | j=6: i=0,2,4 @6 | j=7: i=1,3,5 @8
-    fe_row1(E + 2, a[0], a[2]);
-    fe_row1(E + 4, a[1], a[3]);
-    fe_row2(E + 4, a[0], a[2], a[4]);
-    fe_row2(E + 6, a[1], a[3], a[5]);
-    fe_row3(E + 6, a[0], a[2], a[4], a[6]);
-    fe_row3(E + 8, a[1], a[3], a[5], a[7]);
+    fe_prod(E + 2, a[0], a[2]);
+    fe_prod(E + 4, a[1], a[3]);
+    fe_row2f(E + 4, a[0], a[2], a[4]);
+    fe_row2f(E + 6, a[1], a[3], a[5]);
+    fe_row3f(E + 6, a[0], a[2], a[4], a[6]);
+    fe_row3f(E + 8, a[1], a[3], a[5], a[7]);
+    E[14] = 0; E[15] = 0;
     // S = E + (O << 32): S[0] = 0, S[1] = O[0], S[2..15] = E[2..15] + O[1..14]
     uint32_t S[16], x[8], y[8], s2[8];
     S[0] = 0;

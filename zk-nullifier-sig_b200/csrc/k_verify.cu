@@ -5,10 +5,11 @@ __global__ void __launch_bounds__(128) k_verify_h2c(verify_args a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.n) verify_stage_h2c(i, a);
 }
-__global__ void __launch_bounds__(VB_BLOCK, PLUME_VB_MINBLOCKS) k_verify_muls(verify_args a) {
-    extern __shared__ uint32_t vb_smem[];
+__global__ void __launch_bounds__(PLUME_VM_BLOCK, PLUME_VM_MINBLOCKS) k_verify_muls(verify_args a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < a.n) verify_stage_muls(i, a, VB_TAB(a, i));
+    if (i < a.n)
+        verify_stage_muls(i, a, vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS},
+                          vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS + VB_TAB_WORDS});
 }
 __global__ void __launch_bounds__(128) k_verify_final(verify_args a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -22,7 +23,7 @@ cudaError_t launch_verify_h2c(const verify_args& a, cudaStream_t s) {
     return cudaGetLastError();
 }
 cudaError_t launch_verify_muls(const verify_args& a, cudaStream_t s) {
-    k_verify_muls<<<grid_for(a.n, VB_BLOCK), VB_BLOCK, VB_SMEM_BYTES, s>>>(a);
+    k_verify_muls<<<grid_for(a.n, PLUME_VM_BLOCK), PLUME_VM_BLOCK, 0, s>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_verify_final(const verify_args& a, cudaStream_t s) {
@@ -30,6 +31,5 @@ cudaError_t launch_verify_final(const verify_args& a, cudaStream_t s) {
     return cudaGetLastError();
 }
 cudaError_t kernels_init_verify() {
-    if (VB_SMEM_BYTES == 0) return cudaSuccess;
-    return cudaFuncSetAttribute(k_verify_muls, cudaFuncAttributeMaxDynamicSharedMemorySize, VB_SMEM_BYTES);
+    return cudaSuccess;
 }

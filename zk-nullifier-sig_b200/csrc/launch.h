@@ -22,6 +22,13 @@
 #define VB_SMEM_BYTES (VB_TAB_WORDS * 4 * VB_BLOCK)
 #define VB_TAB(a, i) vb_tab_strided{vb_smem + threadIdx.x, VB_BLOCK}
 #endif
+// the verifier's double-base ladder keeps two tables per thread: always in global scratch
+#ifndef PLUME_VM_BLOCK
+#define PLUME_VM_BLOCK 128
+#endif
+#ifndef PLUME_VM_MINBLOCKS
+#define PLUME_VM_MINBLOCKS 3
+#endif
 
 cudaError_t launch_sign_fixed(const sign_args& a, cudaStream_t s);
 cudaError_t launch_sign_h2c(const sign_args& a, cudaStream_t s);

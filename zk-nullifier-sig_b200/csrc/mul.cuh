@@ -168,3 +168,50 @@ PLUME_DEV jac vb_mul_tab(const sc& k, const Tab& tab, const fe& zg) {
     if (!acc.inf) acc.z = fe_mul(acc.z, zg);
     return acc;
 }
+
+// k1 * P1 + k2 * P2 with shared doublings (Straus): both tables must be expressed on the same
+// isomorphic curve (common denominator zg), see vb_build_table_pair.
+template <class Tab>
+PLUME_DEV jac vb_mul2_tab(const sc& k1, const Tab& tab1, const sc& k2, const Tab& tab2, const fe& zg) {
+    glv_half h[4];
+    glv_split(k1, h[0], h[1]);
+    glv_split(k2, h[2], h[3]);
+    booth_reg b0 = booth_init(h[0]), b1 = booth_init(h[1]), b2 = booth_init(h[2]), b3 = booth_init(h[3]);
+    jac acc = jac_infinity();
+#pragma unroll 1
+    for (int i = 32; i >= 0; i--) {
+#pragma unroll 1
+        for (int j = 0; j < 4; j++) acc = jac_dbl(acc);
+        int d0 = booth_next(b0), d1 = booth_next(b1), d2 = booth_next(b2), d3 = booth_next(b3);
+        // one addition body for the four half-scalars (rolled on purpose: code size)
+#pragma unroll 1
+        for (int q = 0; q < 4; q++) {
+            int d = q == 0 ? d0 : q == 1 ? d1 : q == 2 ? d2 : d3;
+            uint32_t flip = q == 0 ? h[0].neg : q == 1 ? h[1].neg : q == 2 ? h[2].neg : h[3].neg;
+            if (q < 2) acc = vb_add_digit(acc, d, flip, (q & 1) != 0, tab1);
+            else acc = vb_add_digit(acc, d, flip, (q & 1) != 0, tab2);
+        }
+    }
+    if (!acc.inf) acc.z = fe_mul(acc.z, zg);
+    return acc;
+}
+
+// Tables of two affine, on-curve, non-identity points over one common denominator.  P1's table is
+// built first (denominator z1); P2 is moved onto P1's isomorphic curve (x*z1^2, y*z1^3) and its table
+// built there (relative denominator z2); P1's entries are then rescaled by z2.  Returns z1*z2.
+template <class Tab>
+PLUME_DEV fe vb_build_table_pair(const fe& p1x, const fe& p1y, const Tab& tab1, const fe& p2x, const fe& p2y, const Tab& tab2) {
+    fe z1 = vb_build_table(p1x, p1y, tab1);
+    fe z1_2 = fe_sqr(z1);
+    fe qx = fe_mul(p2x, z1_2);
+    fe qy = fe_mul(p2y, fe_mul(z1_2, z1));
+    fe z2 = vb_build_table(qx, qy, tab2);
+    fe z2_2 = fe_sqr(z2), z2_3 = fe_mul(z2_2, z2);
+#pragma unroll 1
+    for (int e = 0; e < 8; e++) {
+        fe x, y;
+        tab1.load(e, x, y);
+        tab1.store(e, fe_mul(x, z2_2), fe_mul(y, z2_3));
+    }
+    return fe_mul(z1, z2);
+}

@@ -397,8 +397,9 @@ PLUME_DEV jac vb_mul_point(const aff& p, const sc& k, const Tab& tab) {
     return vb_mul_tab(k, tab, zg);
 }
 
+// tab1, tab2: two table areas of this thread (global scratch)
 template <class Tab>
-PLUME_DEV void verify_stage_muls(uint32_t i, const verify_args& a, const Tab& tab) {
+PLUME_DEV void verify_stage_muls(uint32_t i, const verify_args& a, const Tab& tab1, const Tab& tab2) {
     aff h = ws_load_affine(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i);
     ws_store_aff(a.ws, a.n, WS_HX, WS_HY, i, h);
     // remember whether h is the identity: WS_RX limb 0
@@ -416,13 +417,18 @@ PLUME_DEV void verify_stage_muls(uint32_t i, const verify_args& a, const Tab& ta
         nul = aff_generator();
     }
     sc mc = sc_neg(c);
-    // A = G*s - pk*c   (lib.rs:101)
+    // A = G*s - pk*c   (lib.rs:101): table walk for the generator, windowed ladder for pk
     jac A = fb_mul(s, a.gtab, a.gw);
-    A = jac_add(A, vb_mul_point(pk, mc, tab));
+    A = jac_add(A, vb_mul_point(pk, mc, tab1));
     ws_store_jac(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i, A);
-    // B = h*s - nul*c  (lib.rs:109)
-    jac B = vb_mul_point(h, s, tab);
-    B = jac_add(B, vb_mul_point(nul, mc, tab));
+    // B = h*s - nul*c  (lib.rs:109): one ladder over both tables (shared doublings)
+    jac B;
+    if (!h.inf && !nul.inf) {
+        fe zg = vb_build_table_pair(h.x, h.y, tab1, nul.x, nul.y, tab2);
+        B = vb_mul2_tab(s, tab1, mc, tab2, zg);
+    } else {
+        B = jac_add(vb_mul_point(h, s, tab1), vb_mul_point(nul, mc, tab1));
+    }
     ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, B);
 }
 
