@@ -218,7 +218,9 @@ def main():
     ctx = plume_b200.PlumeContext(local_rank)
     chunk = ctx.chunk_items
 
-    msgs_h, sk_h, r_h = synth_inputs(seed, rank * n, n)     # this rank's contiguous range of the global batch
+    first, last = plume_b200.shard_range(n * world, rank, world)   # this rank's contiguous range of the global batch
+    assert last - first == n
+    msgs_h, sk_h, r_h = synth_inputs(seed, first, n)
 
     def pinned(a):
         t = torch.from_numpy(a).pin_memory()
@@ -318,12 +320,7 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
-    if dist is not None:
-        t = torch.tensor([dev_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms = float(t[0]), float(t[1])
-    else:
-        e2e_ms = e2e_s * 1e3
+    dev_ms, e2e_ms = plume_b200.reduce_max([dev_ms, e2e_s * 1e3], dist, dev)   # max over ranks
     ops_step_gpu = n * ops_per_item
     value = world * ops_step_gpu * args.steps / (dev_ms * 1e-3)
     e2e_val = world * ops_step_gpu * args.steps / (e2e_ms * 1e-3)
@@ -349,9 +346,8 @@ def main():
             if not torch.equal(D[k].cpu(), H[k]):
                 checks["device_vs_host_api_" + k] = False
     if dist is not None:
-        flag = torch.tensor([1 if all(checks.values()) else 0], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        checks["all_ranks"] = bool(flag.item())
+        checks["all_ranks"] = plume_b200.all_ranks_true(all(checks.values()), dist, dev)
+        checks["shards_tile_batch"] = sum(plume_b200.gather_counts(n, dist, dev)) == n * world
 
     line = {"metric": metric, "value": value, "unit": "ops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -4,7 +4,8 @@ from .api import (DST, ORDER, PlumeContext, PlumeError, PlumeSignature, PlumeSig
                   SecretKey, default_context, encode_pt, hash_to_curve, pack_messages, point_from_bytes,
                   point_to_bytes)
 from ._lib import LIB_PATH, SYMBOLS, load
+from .shard import all_ranks_true, gather_counts, reduce_max, shard_range
 
 __all__ = ["DST", "ORDER", "PlumeContext", "PlumeError", "PlumeSignature", "PlumeSignatureV1Fields", "PlumeSigner",
            "SecretKey", "default_context", "encode_pt", "hash_to_curve", "pack_messages", "point_from_bytes",
-           "point_to_bytes", "LIB_PATH", "SYMBOLS", "load"]
+           "point_to_bytes", "LIB_PATH", "SYMBOLS", "load", "shard_range", "reduce_max", "all_ranks_true", "gather_counts"]

@@ -1,0 +1,42 @@
+//! Raw bindings of include/plume_b200.h (hand-written; the header is the source of truth).
+#![allow(non_camel_case_types)]
+use core::ffi::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct plume_ctx {
+    _private: [u8; 0],
+}
+
+pub const PLUME_OK: c_int = 0;
+pub const PLUME_STATUS_OK: u8 = 0;
+pub const PLUME_STATUS_BAD_R: u8 = 1;
+pub const PLUME_STATUS_BAD_SK: u8 = 2;
+pub const PLUME_STATUS_BAD_C: u8 = 3;
+pub const PLUME_STATUS_ZERO_S: u8 = 4;
+pub const PLUME_STATUS_H_INF: u8 = 5;
+
+extern "C" {
+    pub fn plume_version() -> c_int;
+    pub fn plume_ctx_create(out: *mut *mut plume_ctx, device: c_int, fixed_window_bits: c_int) -> c_int;
+    pub fn plume_ctx_destroy(ctx: *mut plume_ctx);
+    pub fn plume_last_error(ctx: *const plume_ctx) -> *const c_char;
+    pub fn plume_ctx_chunk_items(ctx: *const plume_ctx) -> usize;
+    pub fn plume_sign_batch(
+        ctx: *mut plume_ctx, version: c_int, n: usize, msgs: *const u8, msg_offsets: *const u64, msg_len: usize,
+        sk: *const u8, r: *const u8, pk: *mut u8, nullifier: *mut u8, c: *mut u8, s: *mut u8,
+        r_point: *mut u8, hashed_to_curve_r: *mut u8, status: *mut u8,
+    ) -> c_int;
+    pub fn plume_verify_batch(
+        ctx: *mut plume_ctx, version: c_int, n: usize, msgs: *const u8, msg_offsets: *const u64, msg_len: usize,
+        pk: *const u8, nullifier: *const u8, c: *const u8, s: *const u8,
+        r_point: *const u8, hashed_to_curve_r: *const u8, ok: *mut u8,
+    ) -> c_int;
+    pub fn plume_hash_to_curve_batch(
+        ctx: *mut plume_ctx, n: usize, msgs: *const u8, msg_offsets: *const u64, msg_len: usize, out: *mut u8,
+    ) -> c_int;
+    pub fn plume_sign_batch_device(
+        ctx: *mut plume_ctx, version: c_int, n: usize, msgs: *const u8, msg_offsets: *const u64, msg_len: usize,
+        sk: *const u8, r: *const u8, pk: *mut u8, nullifier: *mut u8, c: *mut u8, s: *mut u8,
+        r_point: *mut u8, hashed_to_curve_r: *mut u8, status: *mut u8, stream: *mut c_void,
+    ) -> c_int;
+}
