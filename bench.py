@@ -185,7 +185,7 @@ def main():
         if rank != 0:
             return 0
         threads = host_threads()
-        sample = args.cpu_sample or max(256, min(n, 1 << 13))
+        sample = args.cpu_sample or max(256, min(n, 2048 * threads))   # ~2-3 s of CPU work per step
         msgs, sk, r = synth_inputs(seed, 0, sample)
         times, ops = [], 0
         for it in range(args.warmup + args.steps):
@@ -370,8 +370,16 @@ def main():
         avg_ms = stage[dom]["ms_total"] / stage[dom]["launches"]
         work_m = WORK_M.get(dom, WORK_M["h2c"] if dom.startswith("h2c") else 640)
         ach = per_launch_items * work_m * LP_PER_M / (avg_ms * 1e-3)
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full summary
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tj = json.load(f)
+            if dom in tj and tj[dom]["items_per_launch"] == per_launch_items:
+                traffic = tj[dom]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         line["roofline"] = {"bound": "int-alu", "kernel": dom, "achieved": ach, "peak": peak_lp, "unit": "limb-products/s",
-                            "frac": ach / peak_lp, "traffic": None,
+                            "frac": ach / peak_lp, "traffic": traffic,
                             "peak_source": "measured in this run: IMAD.WIDE.U32 independent-chain microbenchmark "
                                            "(MEASURED_PEAKS.json carries no INT32 figure)",
                             "algorithmic_work": "%d field multiplications x %d limb-products per item (SURVEY.md 8d), %d items per launch"
@@ -390,7 +398,7 @@ def main():
         # cpu baseline, bounded sample, rank 0 only at N = 1
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
-            sample = args.cpu_sample or max(1024, min(n, 1 << 13))
+            sample = args.cpu_sample or max(1024, min(n, 8192 * threads))   # ~10-20 s of CPU work on all host threads
             ops, dt, out = cpu_run(args.workload, version, msgs_h[:sample], sk_h[:sample], r_h[:sample], threads)
             line["cpu_baseline"] = {"value": ops / dt, "unit": "ops/s", "cores": threads, "kind": "port",
                                     "sample": "first %d items of this workload (%d ops), C restatement of the rust-k256 path "

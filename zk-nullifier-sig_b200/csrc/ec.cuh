@@ -35,45 +35,44 @@ PLUME_DEV bool aff_on_curve(const fe& x, const fe& y) {
     return fe_eq(lhs, rhs);
 }
 
-// 2P, a = 0: 2M + 5S  (no point of order two exists: the group order is odd)
+// 2P, a = 0: 2M + 5S  (no point of order two exists: the group order is odd).
+// Statement order is chosen for short live ranges (the multiplier is an opaque call to the compiler,
+// so it keeps this order): at most five field elements are alive at any point.
 PLUME_DEV jac jac_dbl(const jac& p) {
     if (p.inf) return p;
-    fe A = fe_sqr(p.x);
-    fe B = fe_sqr(p.y);
-    fe C = fe_sqr(B);
-    fe t = fe_sqr(fe_add(p.x, B));
-    fe D = fe_dbl(fe_sub(fe_sub(t, A), C));
-    fe E = fe_add(fe_dbl(A), A);
-    fe F = fe_sqr(E);
     jac r;
-    r.x = fe_sub(F, fe_dbl(D));
+    r.z = fe_dbl(fe_mul(p.y, p.z));          // Z3 = 2*Y*Z          (Z dead)
+    fe A = fe_sqr(p.x);
+    fe B = fe_sqr(p.y);                      //                      (Y dead)
+    fe t = fe_sqr(fe_add(p.x, B));           //                      (X dead)
+    fe C = fe_sqr(B);                        //                      (B dead)
+    fe D = fe_dbl(fe_sub(fe_sub(t, A), C));  // 2*((X+B)^2 - A - C)  (t dead)
+    fe E = fe_add(fe_dbl(A), A);             // 3*A                  (A dead)
+    r.x = fe_sub(fe_sqr(E), fe_dbl(D));      // E^2 - 2*D
     fe C8 = fe_dbl(fe_dbl(fe_dbl(C)));
     r.y = fe_sub(fe_mul(E, fe_sub(D, r.x)), C8);
-    r.z = fe_dbl(fe_mul(p.y, p.z));
     r.inf = 0;
     return r;
 }
 
-// P + Q, Q affine: 8M + 3S.  `zscale` (optional out) receives H so that Z3 = Z1 * H.
+// P + Q, Q affine: 8M + 3S, ordered for short live ranges as well.
 PLUME_DEV jac jac_add_aff(const jac& p, const fe& qx, const fe& qy, uint32_t qinf) {
     if (qinf) return p;
     if (p.inf) { jac r; r.x = qx; r.y = qy; r.z = fe_one(); r.inf = 0; return r; }
     fe z2 = fe_sqr(p.z);
-    fe u2 = fe_mul(qx, z2);
-    fe s2 = fe_mul(qy, fe_mul(p.z, z2));
-    fe H = fe_sub(u2, p.x);
-    fe R = fe_sub(s2, p.y);
+    fe H = fe_sub(fe_mul(qx, z2), p.x);                  // U2 - X1            (qx dead)
+    fe R = fe_sub(fe_mul(qy, fe_mul(p.z, z2)), p.y);     // S2 - Y1            (qy, z2 dead)
     if (fe_is_zero(H)) {
         if (fe_is_zero(R)) return jac_dbl(p);
         return jac_infinity();
     }
-    fe H2 = fe_sqr(H);
-    fe H3 = fe_mul(H, H2);
-    fe V = fe_mul(p.x, H2);
     jac r;
+    r.z = fe_mul(p.z, H);                                //                    (Z1 dead)
+    fe H2 = fe_sqr(H);
+    fe H3 = fe_mul(H, H2);                               //                    (H dead)
+    fe V = fe_mul(p.x, H2);                              //                    (X1, H2 dead)
     r.x = fe_sub(fe_sub(fe_sqr(R), H3), fe_dbl(V));
     r.y = fe_sub(fe_mul(R, fe_sub(V, r.x)), fe_mul(p.y, H3));
-    r.z = fe_mul(p.z, H);
     r.inf = 0;
     return r;
 }
