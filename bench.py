@@ -185,7 +185,13 @@ def main():
         if rank != 0:
             return 0
         threads = host_threads()
-        sample = args.cpu_sample or max(256, min(n, 2048 * threads))   # ~2-3 s of CPU work per step
+        if args.cpu_sample:
+            sample = args.cpu_sample
+        else:   # calibrate, then size each step for ~4 s so that warmup + steps stay within a couple of minutes
+            cal = 16 * threads
+            m0, s0, r0 = synth_inputs(seed, 0, cal)
+            _, dt, _ = cpu_run(args.workload, version, m0, s0, r0, threads)
+            sample = int(max(cal, min(n, 4.0 * cal / max(dt, 1e-3))))
         msgs, sk, r = synth_inputs(seed, 0, sample)
         times, ops = [], 0
         for it in range(args.warmup + args.steps):
@@ -398,7 +404,12 @@ def main():
         # cpu baseline, bounded sample, rank 0 only at N = 1
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
-            sample = args.cpu_sample or max(1024, min(n, 8192 * threads))   # ~10-20 s of CPU work on all host threads
+            if args.cpu_sample:
+                sample = args.cpu_sample
+            else:   # calibrate on a small slice, then size the sample for ~15 s of wall time on all host threads
+                cal = min(n, 16 * threads)
+                ops, dt, _ = cpu_run(args.workload, version, msgs_h[:cal], sk_h[:cal], r_h[:cal], threads)
+                sample = int(max(cal, min(n, 15.0 * cal / max(dt, 1e-3))))
             ops, dt, out = cpu_run(args.workload, version, msgs_h[:sample], sk_h[:sample], r_h[:sample], threads)
             line["cpu_baseline"] = {"value": ops / dt, "unit": "ops/s", "cores": threads, "kind": "port",
                                     "sample": "first %d items of this workload (%d ops), C restatement of the rust-k256 path "

@@ -278,7 +278,7 @@ int plume_ctx_create(plume_ctx** out, int device, int fixed_window_bits) {
     plume_ctx* c = new plume_ctx();
     c->device = device;
     c->gw = w;
-    c->chunk = env_size("PLUME_CHUNK_ITEMS", (size_t)1 << 18);
+    c->chunk = env_size("PLUME_CHUNK_ITEMS", (size_t)1 << 19);  // 4096 blocks = 6.9 waves of 148 SMs x 4 blocks: 1 % tail
     c->binv_k = (uint32_t)env_size("PLUME_BINV_K", 16);
     struct Guard { plume_ctx* c; ~Guard() { if (c) plume_ctx_destroy(c); } } guard{c};
     for (Lane& L : c->lanes) {
