@@ -156,12 +156,76 @@ PLUME_DEV fe fe_sub(const fe& a, const fe& b) {
     return r;
 }
 
-// Rows of the schoolbook product: acc += (a0, a1, ..) * b as chained 64-bit lanes (one IMAD.WIDE.U32.X
-// per lane).  Words a row touches for the first time are pure outputs (multiply-add with a zero
-// addend), so no accumulator ever needs a zeroing move:
+// Rows of the schoolbook product: acc += (a0, a1, ..) * b as chained 64-bit lanes.  Words a row
+// touches for the first time are pure outputs, so no accumulator ever needs a zeroing move:
 //   fe_row4t : lanes 0..2 accumulate, lane 3 = (acc[6] += .., acc[7] fresh); no carry out of a fresh word
 //   fe_row4c : lanes 0..3 accumulate, the carry out is written to the fresh word acc[8]
 //   fe_rowNf : N lanes, the first N-1 accumulate, the last lane is entirely fresh (squaring)
+//
+// A lane can be computed two ways.  "Hard": one IMAD.WIDE.U32.X (multiply + 64-bit add + carry in/out).
+// "Soft": a plain IMAD.WIDE.U32 product followed by two IADD3.X inside the same carry chain.  The hard form
+// issues at half the rate of a plain IMAD.WIDE (profiles/r01_imad_rates.md), which suggested moving the odd
+// lanes to the ALU pipe; measured on the B200 that is 16 % SLOWER (k_sign_varbase 20.3 ms vs 17.4 ms per 2^19
+// items): the integer pipes do not overlap enough to pay for the two extra instructions.  The soft rows are
+// kept behind -DPLUME_SOFT_LANES=1 as the record of that experiment; the default is all-hard.
+#ifndef PLUME_SOFT_LANES
+#define PLUME_SOFT_LANES 0
+#endif
+PLUME_DEV void fe_prod(uint32_t* acc, uint32_t a, uint32_t b) {  // plain 64-bit product (IMAD.WIDE.U32, no carry)
+    uint64_t p = (uint64_t)a * b;
+    acc[0] = (uint32_t)p;
+    acc[1] = (uint32_t)(p >> 32);
+}
+#if PLUME_SOFT_LANES
+PLUME_DEV void fe_row4t(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+    uint32_t p1[2], p3[2];
+    fe_prod(p1, a1, b);
+    fe_prod(p3, a3, b);
+    asm("mad.lo.cc.u32 %0, %8, %14, %0;\n\tmadc.hi.cc.u32 %1, %8, %14, %1;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\taddc.cc.u32 %3, %3, %11;\n\t"
+        "madc.lo.cc.u32 %4, %9, %14, %4;\n\tmadc.hi.cc.u32 %5, %9, %14, %5;\n\t"
+        "addc.cc.u32 %6, %6, %12;\n\taddc.u32 %7, %13, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "=r"(acc[7])
+        : "r"(a0), "r"(a2), "r"(p1[0]), "r"(p1[1]), "r"(p3[0]), "r"(p3[1]), "r"(b));
+}
+PLUME_DEV void fe_row4c(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+    uint32_t p1[2], p3[2];
+    fe_prod(p1, a1, b);
+    fe_prod(p3, a3, b);
+    asm("mad.lo.cc.u32 %0, %9, %15, %0;\n\tmadc.hi.cc.u32 %1, %9, %15, %1;\n\t"
+        "addc.cc.u32 %2, %2, %11;\n\taddc.cc.u32 %3, %3, %12;\n\t"
+        "madc.lo.cc.u32 %4, %10, %15, %4;\n\tmadc.hi.cc.u32 %5, %10, %15, %5;\n\t"
+        "addc.cc.u32 %6, %6, %13;\n\taddc.cc.u32 %7, %7, %14;\n\taddc.u32 %8, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=r"(acc[8])
+        : "r"(a0), "r"(a2), "r"(p1[0]), "r"(p1[1]), "r"(p3[0]), "r"(p3[1]), "r"(b));
+}
+PLUME_DEV void fe_row2f(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t b) {
+    uint32_t p1[2];
+    fe_prod(p1, a1, b);
+    asm("mad.lo.cc.u32 %0, %4, %7, %0;\n\tmadc.hi.cc.u32 %1, %4, %7, %1;\n\taddc.cc.u32 %2, %5, 0;\n\taddc.u32 %3, %6, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]) : "r"(a0), "r"(p1[0]), "r"(p1[1]), "r"(b));
+}
+PLUME_DEV void fe_row3f(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b) {
+    uint32_t p1[2], p2[2];
+    fe_prod(p1, a1, b);
+    fe_prod(p2, a2, b);
+    asm("mad.lo.cc.u32 %0, %6, %11, %0;\n\tmadc.hi.cc.u32 %1, %6, %11, %1;\n\taddc.cc.u32 %2, %2, %7;\n\taddc.cc.u32 %3, %3, %8;\n\t"
+        "addc.cc.u32 %4, %9, 0;\n\taddc.u32 %5, %10, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "=r"(acc[4]), "=r"(acc[5])
+        : "r"(a0), "r"(p1[0]), "r"(p1[1]), "r"(p2[0]), "r"(p2[1]), "r"(b));
+}
+PLUME_DEV void fe_row4f(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+    uint32_t p1[2], p3[2];
+    fe_prod(p1, a1, b);
+    fe_prod(p3, a3, b);
+    asm("mad.lo.cc.u32 %0, %8, %14, %0;\n\tmadc.hi.cc.u32 %1, %8, %14, %1;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\taddc.cc.u32 %3, %3, %11;\n\t"
+        "madc.lo.cc.u32 %4, %9, %14, %4;\n\tmadc.hi.cc.u32 %5, %9, %14, %5;\n\t"
+        "addc.cc.u32 %6, %12, 0;\n\taddc.u32 %7, %13, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "=r"(acc[6]), "=r"(acc[7])
+        : "r"(a0), "r"(a2), "r"(p1[0]), "r"(p1[1]), "r"(p3[0]), "r"(p3[1]), "r"(b));
+}
+#else
 PLUME_DEV void fe_row4t(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
     asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\tmadc.hi.cc.u32 %1, %8, %12, %1;\n\t"
         "madc.lo.cc.u32 %2, %9, %12, %2;\n\tmadc.hi.cc.u32 %3, %9, %12, %3;\n\t"
@@ -195,11 +259,7 @@ PLUME_DEV void fe_row4f(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, ui
         : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "=r"(acc[6]), "=r"(acc[7])
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
 }
-PLUME_DEV void fe_prod(uint32_t* acc, uint32_t a, uint32_t b) {  // plain 64-bit product (IMAD.WIDE.U32, no carry)
-    uint64_t p = (uint64_t)a * b;
-    acc[0] = (uint32_t)p;
-    acc[1] = (uint32_t)(p >> 32);
-}
+#endif
 
 // t[0..7] = x[0..7] + y[0..7] + cin, returns the carry out (cin, cout in {0,1}); long additions are
 // stitched from these so that every statement stays under the 30-operand limit of inline asm
@@ -304,6 +364,25 @@ PLUME_DEV void fe_sqr_wide(uint32_t* T, const uint32_t* a) {
     D[0] = 0;
 #pragma unroll
     for (int i = 1; i < 16; i++) D[i] = __funnelshift_l(S[i - 1], S[i], 1);
+#if PLUME_SOFT_LANES
+    {
+        uint32_t q1[2], q3[2], q5[2], q7[2];
+        fe_prod(q1, a[1], a[1]); fe_prod(q3, a[3], a[3]); fe_prod(q5, a[5], a[5]); fe_prod(q7, a[7], a[7]);
+        asm("mad.lo.cc.u32 %0, %9, %9, %0;\n\tmadc.hi.cc.u32 %1, %9, %9, %1;\n\t"
+            "addc.cc.u32 %2, %2, %11;\n\taddc.cc.u32 %3, %3, %12;\n\t"
+            "madc.lo.cc.u32 %4, %10, %10, %4;\n\tmadc.hi.cc.u32 %5, %10, %10, %5;\n\t"
+            "addc.cc.u32 %6, %6, %13;\n\taddc.cc.u32 %7, %7, %14;\n\taddc.u32 %8, 0, 0;"
+            : "+r"(D[0]), "+r"(D[1]), "+r"(D[2]), "+r"(D[3]), "+r"(D[4]), "+r"(D[5]), "+r"(D[6]), "+r"(D[7]), "=r"(c)
+            : "r"(a[0]), "r"(a[2]), "r"(q1[0]), "r"(q1[1]), "r"(q3[0]), "r"(q3[1]));
+        asm("add.cc.u32 %8, %8, 0xffffffff;\n\t"
+            "madc.lo.cc.u32 %0, %9, %9, %0;\n\tmadc.hi.cc.u32 %1, %9, %9, %1;\n\t"
+            "addc.cc.u32 %2, %2, %11;\n\taddc.cc.u32 %3, %3, %12;\n\t"
+            "madc.lo.cc.u32 %4, %10, %10, %4;\n\tmadc.hi.cc.u32 %5, %10, %10, %5;\n\t"
+            "addc.cc.u32 %6, %6, %13;\n\taddc.u32 %7, %7, %14;"
+            : "+r"(D[8]), "+r"(D[9]), "+r"(D[10]), "+r"(D[11]), "+r"(D[12]), "+r"(D[13]), "+r"(D[14]), "+r"(D[15]), "+r"(c)
+            : "r"(a[4]), "r"(a[6]), "r"(q5[0]), "r"(q5[1]), "r"(q7[0]), "r"(q7[1]));
+    }
+#else
     asm("mad.lo.cc.u32 %0, %9, %9, %0;\n\tmadc.hi.cc.u32 %1, %9, %9, %1;\n\t"
         "madc.lo.cc.u32 %2, %10, %10, %2;\n\tmadc.hi.cc.u32 %3, %10, %10, %3;\n\t"
         "madc.lo.cc.u32 %4, %11, %11, %4;\n\tmadc.hi.cc.u32 %5, %11, %11, %5;\n\t"
@@ -317,6 +396,7 @@ PLUME_DEV void fe_sqr_wide(uint32_t* T, const uint32_t* a) {
         "madc.lo.cc.u32 %6, %12, %12, %6;\n\tmadc.hi.u32 %7, %12, %12, %7;"
         : "+r"(D[8]), "+r"(D[9]), "+r"(D[10]), "+r"(D[11]), "+r"(D[12]), "+r"(D[13]), "+r"(D[14]), "+r"(D[15]), "+r"(c)
         : "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+#endif
 #pragma unroll
     for (int i = 0; i < 16; i++) T[i] = D[i];
 }
@@ -325,6 +405,29 @@ PLUME_DEV void fe_sqr_wide(uint32_t* T, const uint32_t* a) {
 PLUME_DEV fe fe_reduce512(const uint32_t* T) {
     const uint32_t* h = T + 8;
     uint32_t A[9], Q[9];
+#if PLUME_SOFT_LANES
+    {
+        // even lanes: A = T_lo + sum_k h_{2k}*977*2^(64k); lanes 1 and 3 as plain products added in
+        uint32_t e1[2], e3[2], o1[2], o3[2];
+        fe_prod(e1, h[2], FE_C0); fe_prod(e3, h[6], FE_C0);
+        asm("mad.lo.cc.u32 %0, %9, 977, %15;\n\tmadc.hi.cc.u32 %1, %9, 977, %16;\n\t"
+            "addc.cc.u32 %2, %17, %11;\n\taddc.cc.u32 %3, %18, %12;\n\t"
+            "madc.lo.cc.u32 %4, %10, 977, %19;\n\tmadc.hi.cc.u32 %5, %10, 977, %20;\n\t"
+            "addc.cc.u32 %6, %21, %13;\n\taddc.cc.u32 %7, %22, %14;\n\taddc.u32 %8, 0, 0;"
+            : "=&r"(A[0]), "=&r"(A[1]), "=&r"(A[2]), "=&r"(A[3]), "=&r"(A[4]), "=&r"(A[5]), "=&r"(A[6]), "=&r"(A[7]), "=&r"(A[8])
+            : "r"(h[0]), "r"(h[4]), "r"(e1[0]), "r"(e1[1]), "r"(e3[0]), "r"(e3[1]),
+              "r"(T[0]), "r"(T[1]), "r"(T[2]), "r"(T[3]), "r"(T[4]), "r"(T[5]), "r"(T[6]), "r"(T[7]));
+        // odd lanes (offset one limb): Q lane k = h_{2k+1}*977 + (h_{2k} + h_{2k+1}*2^32)
+        fe_prod(o1, h[3], FE_C0); fe_prod(o3, h[7], FE_C0);
+        asm("mad.lo.cc.u32 %0, %10, 977, %9;\n\tmadc.hi.cc.u32 %1, %10, 977, %10;\n\t"
+            "addc.cc.u32 %2, %11, %17;\n\taddc.cc.u32 %3, %12, %18;\n\t"
+            "madc.lo.cc.u32 %4, %14, 977, %13;\n\tmadc.hi.cc.u32 %5, %14, 977, %14;\n\t"
+            "addc.cc.u32 %6, %15, %19;\n\taddc.cc.u32 %7, %16, %20;\n\taddc.u32 %8, 0, 0;"
+            : "=&r"(Q[0]), "=&r"(Q[1]), "=&r"(Q[2]), "=&r"(Q[3]), "=&r"(Q[4]), "=&r"(Q[5]), "=&r"(Q[6]), "=&r"(Q[7]), "=&r"(Q[8])
+            : "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]),
+              "r"(o1[0]), "r"(o1[1]), "r"(o3[0]), "r"(o3[1]));
+    }
+#else
     // even lanes: A = T_lo + sum_k h_{2k}*977*2^(64k)
     asm("mad.lo.cc.u32 %0, %9, 977, %13;\n\tmadc.hi.cc.u32 %1, %9, 977, %14;\n\t"
         "madc.lo.cc.u32 %2, %10, 977, %15;\n\tmadc.hi.cc.u32 %3, %10, 977, %16;\n\t"
@@ -340,6 +443,7 @@ PLUME_DEV fe fe_reduce512(const uint32_t* T) {
         "madc.lo.cc.u32 %6, %16, 977, %15;\n\tmadc.hi.cc.u32 %7, %16, 977, %16;\n\taddc.u32 %8, 0, 0;"
         : "=&r"(Q[0]), "=&r"(Q[1]), "=&r"(Q[2]), "=&r"(Q[3]), "=&r"(Q[4]), "=&r"(Q[5]), "=&r"(Q[6]), "=&r"(Q[7]), "=&r"(Q[8])
         : "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]));
+#endif
     // R = A + (Q << 32): 10 limbs
     uint32_t R[10];
     R[0] = A[0];
