@@ -101,6 +101,8 @@ PLUME_DEV fe fe_mul(const fe& a, const fe& b) {
     return fe_reduce512(t);
 }
 PLUME_DEV fe fe_sqr(const fe& a) { return fe_mul(a, a); }
+PLUME_DEV fe fe_mul_inl(const fe& a, const fe& b) { return fe_mul(a, b); }
+PLUME_DEV fe fe_sqr_inl(const fe& a) { return fe_mul(a, a); }
 
 #else
 // ------------------------------------------------------------------------------------------------
@@ -474,15 +476,28 @@ PLUME_DEV fe fe_reduce512(const uint32_t* T) {
 // The two big bodies are real functions (not inlined): every point formula calls them 7-11 times and
 // the instruction cache, not the register file, is what the inlined version ran out of
 // (profiles/r01_sign_varbase_v0.md: 2.6 "no instruction" stall cycles per issued instruction).
-PLUME_MULFN fe fe_mul(fe a, fe b) {
+PLUME_DEV fe fe_mul_inl(const fe& a, const fe& b) {
     uint32_t T[16];
     fe_mul_wide(T, a.v, b.v);
     return fe_reduce512(T);
 }
-PLUME_MULFN fe fe_sqr(fe a) {
+PLUME_DEV fe fe_sqr_inl(const fe& a) {
     uint32_t T[16];
     fe_sqr_wide(T, a.v);
     return fe_reduce512(T);
+}
+PLUME_MULFN fe fe_mul(fe a, fe b) { return fe_mul_inl(a, b); }
+PLUME_MULFN fe fe_sqr(fe a) { return fe_sqr_inl(a); }
+// a^(2^n) as ONE call: the exponentiation ladders (inversion, square roots) run 250+ squarings in a row, and
+// paying the call marshalling per squaring is a fifth of their cost
+PLUME_MULFN fe fe_sqrn(fe a, int n) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+        uint32_t T[16];
+        fe_sqr_wide(T, a.v);
+        a = fe_reduce512(T);
+    }
+    return a;
 }
 #endif  // device versions
 
@@ -521,12 +536,13 @@ PLUME_DEV fe fe_cmov(const fe& a, const fe& b, bool pick_b) {
     return r;
 }
 
+#ifdef PLUME_HOSTSIM
 // a^(2^n)
 PLUME_DEV fe fe_sqrn(fe a, int n) {
-#pragma unroll 1
     for (int i = 0; i < n; i++) a = fe_sqr(a);
     return a;
 }
+#endif
 
 // r = a * k for a small k   (plain 64-bit arithmetic: a handful of uses in the SSWU map)
 PLUME_DEV fe fe_mul_small(const fe& a, uint32_t k) {

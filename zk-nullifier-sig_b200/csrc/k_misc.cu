@@ -1,7 +1,7 @@
 // k_misc.cu -- hash-to-curve-only pipeline, batched inversion, generator table, IMAD microbenchmark.
 #include "launch.h"
 
-__global__ void __launch_bounds__(128) k_h2c_map(h2c_args a) {
+__global__ void __launch_bounds__(128, PLUME_H2C_MINBLOCKS) k_h2c_map(h2c_args a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.n) h2c_stage_map(i, a);
 }

@@ -5,7 +5,7 @@ __global__ void __launch_bounds__(128) k_sign_fixed(sign_args a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.n) sign_stage_fixed(i, a);
 }
-__global__ void __launch_bounds__(128) k_sign_h2c(sign_args a) {
+__global__ void __launch_bounds__(128, PLUME_H2C_MINBLOCKS) k_sign_h2c(sign_args a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.n) sign_stage_h2c(i, a);
 }

@@ -1,7 +1,7 @@
 // k_verify.cu -- stage kernels of the verification pipeline (bodies in stages.cuh).
 #include "launch.h"
 
-__global__ void __launch_bounds__(128) k_verify_h2c(verify_args a) {
+__global__ void __launch_bounds__(128, PLUME_H2C_MINBLOCKS) k_verify_h2c(verify_args a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.n) verify_stage_h2c(i, a);
 }

@@ -27,6 +27,10 @@
 #define VB_SMEM_BYTES (VB_TAB_WORDS * 4 * VB_BLOCK)
 #define VB_TAB(a, i) vb_tab_strided{vb_smem + threadIdx.x, VB_BLOCK}
 #endif
+// hash-to-curve kernels: register cap (blocks of 128 threads per SM)
+#ifndef PLUME_H2C_MINBLOCKS
+#define PLUME_H2C_MINBLOCKS 4
+#endif
 // the verifier's double-base ladder keeps two tables per thread: always in global scratch
 #ifndef PLUME_VM_BLOCK
 #define PLUME_VM_BLOCK 128
