@@ -154,7 +154,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sign_verify", choices=["sign_verify", "sign", "verify", "h2c", "config4"])
+    ap.add_argument("--workload", default="sign_verify", choices=["sign_verify", "sign", "verify", "h2c", "config4", "sec1"])
     ap.add_argument("--log2-batch", type=int, default=None, help="items per GPU per step = 2^B")
     ap.add_argument("--cpu-sample", type=int, default=0, help="items of the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -166,16 +166,19 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     version = 2 if args.workload == "config4" else 1
+    if args.workload == "sec1" and args.impl == "reference":
+        raise SystemExit("--workload sec1 has no reference arm (the CPU path is timed on the 64-byte form)")
     lg = args.log2_batch if args.log2_batch is not None else {"config4": 21, "h2c": 22}.get(args.workload, 20)
     n = 1 << lg
     seed = {"sign": 2, "verify": 3, "config4": 4, "h2c": 5}.get(args.workload, 2)
-    ops_per_item = 2 if args.workload in ("sign_verify", "config4") else 1
+    ops_per_item = 2 if args.workload in ("sign_verify", "config4", "sec1") else 1
     metric = "PLUME sigs+verifies/sec (batch, bit-exact)"
     cfg = {"workload": {"sign_verify": "BASELINE configs[1]+[2]: batch 2^%d PLUME V1 sign then V1 verify of the same batch" % lg,
                         "sign": "BASELINE configs[1]: batch 2^%d PLUME V1 sign" % lg,
                         "verify": "BASELINE configs[2]: batch 2^%d PLUME V1 verify" % lg,
                         "config4": "BASELINE configs[3]: batch 2^%d per GPU PLUME V2 sign+verify, range-split" % lg,
-                        "h2c": "BASELINE configs[4]: hash_to_curve-only, 2^%d 65-byte preimages" % lg}[args.workload],
+                        "h2c": "BASELINE configs[4]: hash_to_curve-only, 2^%d 65-byte preimages" % lg,
+                        "sec1": "SURVEY 8f-2: batch 2^%d PLUME V1 sign then verify on SEC1-compressed (33-byte) points, host API only" % lg}[args.workload],
            "version": "V%d" % version, "items_per_gpu_per_step": n, "msg_bytes": 32,
            "parallelism": "range-split x%d, no data-path collective" % world,
            "l2": "working set per step (inputs+outputs+workspace > 500 MB) exceeds the 126 MB L2; no explicit flush"}
@@ -241,14 +244,20 @@ def main():
     D = {k: H[k].to(dev) for k in ("msgs", "sk", "r")}
     for k in ("pk", "nullifier", "c", "s", "r_point", "hashed_to_curve_r", "status", "ok"):
         D[k] = torch.empty_like(H[k], device=dev)
+    if args.workload == "sec1":   # 33-byte slots next to the 64-byte buffers
+        for k in ("pk", "nullifier", "r_point", "hashed_to_curve_r"):
+            H[k + "33"] = torch.empty((n, 33), dtype=torch.uint8).pin_memory()
+            D[k + "33"] = torch.empty((n, 33), dtype=torch.uint8, device=dev)
+            D[k + "ok"] = torch.empty(n, dtype=torch.uint8, device=dev)
     if args.workload == "h2c":
         pre_h = np.ascontiguousarray(np.concatenate([msgs_h, np.full((n, 1), 2, np.uint8), sk_h], axis=1))
         H["pre"] = pinned(pre_h); H["h"] = torch.empty((n, 64), dtype=torch.uint8).pin_memory()
         D["pre"] = H["pre"].to(dev); D["h"] = torch.empty((n, 64), dtype=torch.uint8, device=dev)
     stream = torch.cuda.Stream(device=dev)
     sp = stream.cuda_stream
-    do_sign = args.workload in ("sign", "sign_verify", "config4", "verify")
-    do_verify = args.workload in ("verify", "sign_verify", "config4")
+    do_sign = args.workload in ("sign", "sign_verify", "config4", "verify", "sec1")
+    do_verify = args.workload in ("verify", "sign_verify", "config4", "sec1")
+    PTS = ("pk", "nullifier", "r_point", "hashed_to_curve_r")
 
     def ptr(t, off_items=0, width=None):
         return t.data_ptr() + off_items * (width if width is not None else (t.shape[1] if t.dim() > 1 else 1))
@@ -263,6 +272,11 @@ def main():
                 ctx.sign_batch_device(version, cn, ptr(D["msgs"], i0), 0, 32, ptr(D["sk"], i0), ptr(D["r"], i0), ptr(D["pk"], i0),
                                       ptr(D["nullifier"], i0), ptr(D["c"], i0), ptr(D["s"], i0), ptr(D["r_point"], i0),
                                       ptr(D["hashed_to_curve_r"], i0), ptr(D["status"], i0), sp)
+            if args.workload == "sec1":   # sign -> compress the four points -> decompress them -> verify
+                for k in PTS:
+                    ctx.points_compress_device(cn, ptr(D[k], i0), ptr(D[k + "33"], i0), sp)
+                for k in PTS:
+                    ctx.points_decompress_device(cn, ptr(D[k + "33"], i0), ptr(D[k], i0), ptr(D[k + "ok"], i0), sp)
             if verify:
                 ctx.verify_batch_device(version, cn, ptr(D["msgs"], i0), 0, 32, ptr(D["pk"], i0), ptr(D["nullifier"], i0),
                                         ptr(D["c"], i0), ptr(D["s"], i0), ptr(D["r_point"], i0), ptr(D["hashed_to_curve_r"], i0),
@@ -271,6 +285,12 @@ def main():
     def step_host(sign=True, verify=True):
         if args.workload == "h2c":
             ctx.hash_to_curve_batch_ptr(n, ptr(H["pre"]), 0, 65, ptr(H["h"]))
+            return
+        if args.workload == "sec1":
+            ctx.sign_batch_sec1_ptr(version, n, ptr(H["msgs"]), 0, 32, ptr(H["sk"]), ptr(H["r"]), ptr(H["pk33"]), ptr(H["nullifier33"]),
+                                    ptr(H["c"]), ptr(H["s"]), ptr(H["r_point33"]), ptr(H["hashed_to_curve_r33"]), ptr(H["status"]))
+            ctx.verify_batch_sec1_ptr(version, n, ptr(H["msgs"]), 0, 32, ptr(H["pk33"]), ptr(H["nullifier33"]), ptr(H["c"]), ptr(H["s"]),
+                                      ptr(H["r_point33"]), ptr(H["hashed_to_curve_r33"]), ptr(H["ok"]))
             return
         if sign:
             ctx.sign_batch_ptr(version, n, ptr(H["msgs"]), 0, 32, ptr(H["sk"]), ptr(H["r"]), ptr(H["pk"]), ptr(H["nullifier"]),
@@ -336,10 +356,11 @@ def main():
         h2d, d2h = n * 65, n * 64
     else:
         h2d = d2h = 0
+        pt = 33 if args.workload == "sec1" else 64
         if timed_sign:
-            h2d += n * 96; d2h += n * (64 * 4 + 64 + 1)
+            h2d += n * 96; d2h += n * (pt * 4 + 64 + 1)
         if do_verify:
-            h2d += n * (32 + 64 * 4 + 64); d2h += n
+            h2d += n * (32 + pt * 4 + 64); d2h += n
 
     # ---- correctness inside the run: every status OK, every signature verifies; strided bit-exact sample vs the oracle
     checks = {}
@@ -348,7 +369,8 @@ def main():
             checks["sign_status_ok"] = int((D["status"] == 0).sum().item()) == n and int((H["status"] == 0).sum().item()) == n
         if do_verify:
             checks["verify_all_true"] = int(D["ok"].sum().item()) == n and int(H["ok"].sum().item()) == n
-        for k in ("pk", "nullifier", "c", "s", "r_point", "hashed_to_curve_r"):
+        for k in (("c", "s", "pk33", "nullifier33", "r_point33", "hashed_to_curve_r33") if args.workload == "sec1"
+                  else ("pk", "nullifier", "c", "s", "r_point", "hashed_to_curve_r")):
             if not torch.equal(D[k].cpu(), H[k]):
                 checks["device_vs_host_api_" + k] = False
     if dist is not None:
@@ -397,7 +419,8 @@ def main():
                                    "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}
         # whole-step view: all kernels of the step against the same peak
         step_work = {"sign_verify": WORK_M["sign"] + WORK_M["verify"], "config4": WORK_M["sign"] + WORK_M["verify"],
-                     "sign": WORK_M["sign"], "verify": WORK_M["verify"], "h2c": WORK_M["h2c"]}[args.workload]
+                     "sign": WORK_M["sign"], "verify": WORK_M["verify"], "h2c": WORK_M["h2c"],
+                     "sec1": WORK_M["sign"] + WORK_M["verify"] + 4 * 270}[args.workload]   # + four square roots
         line["roofline"]["whole_step_frac"] = (n * step_work * LP_PER_M * args.steps / (dev_ms * 1e-3)) / peak_lp
         line["stages"] = stage
         line["clocks"] = clocks
@@ -414,7 +437,7 @@ def main():
             line["cpu_baseline"] = {"value": ops / dt, "unit": "ops/s", "cores": threads, "kind": "port",
                                     "sample": "first %d items of this workload (%d ops), C restatement of the rust-k256 path "
                                               "(cargo/rustc unavailable), %d pthreads, %.1f s" % (sample, ops, threads, dt)}
-            if out is not None and do_sign:
+            if out is not None and do_sign and args.workload != "sec1":
                 same = all(np.array_equal(H[k][:sample].numpy(), out[k]) for k in
                            ("pk", "nullifier", "c", "s", "r_point", "hashed_to_curve_r", "status"))
                 line["checks"]["bit_exact_vs_oracle_first_%d" % sample] = bool(same)

@@ -111,6 +111,31 @@ int plume_hash_to_curve_batch(plume_ctx* ctx, size_t n,
                               const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
                               uint8_t* out);
 
+/*
+ * SEC1-compressed wire form: 33-byte slots, `02/03 || x` for a finite point (what
+ * `to_encoded_point(true)` yields, rust-k256/src/utils.rs:23-25; the form the JS binding exchanges,
+ * javascript/src/lib.rs:97-117) and `00` followed by 32 zero bytes for the identity.
+ *   plume_points_compress_batch     n x 64 -> n x 33 (no validation)
+ *   plume_points_decompress_batch   n x 33 -> n x 64 and ok[i]: 1 when the slot decodes the way k256's
+ *                                   AffinePoint decoding accepts it (prefix, x < p, x^3 + 7 a square), else 0 (point zeroed)
+ *   plume_sign_batch_sec1           plume_sign_batch with 33-byte point outputs (r_point33 / hashed_to_curve_r33 may be NULL)
+ *   plume_verify_batch_sec1         plume_verify_batch on 33-byte points; a slot that does not decode gives ok = 0
+ */
+int plume_points_compress_batch(plume_ctx* ctx, size_t n, const uint8_t* in64, uint8_t* out33);
+int plume_points_decompress_batch(plume_ctx* ctx, size_t n, const uint8_t* in33, uint8_t* out64, uint8_t* ok);
+/* device-pointer forms of the two conversions (work enqueued on `stream`) */
+int plume_points_compress_batch_device(plume_ctx* ctx, size_t n, const uint8_t* in64, uint8_t* out33, void* stream);
+int plume_points_decompress_batch_device(plume_ctx* ctx, size_t n, const uint8_t* in33, uint8_t* out64, uint8_t* ok, void* stream);
+int plume_sign_batch_sec1(plume_ctx* ctx, int version, size_t n,
+                          const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                          const uint8_t* sk, const uint8_t* r,
+                          uint8_t* pk33, uint8_t* nullifier33, uint8_t* c, uint8_t* s,
+                          uint8_t* r_point33, uint8_t* hashed_to_curve_r33, uint8_t* status);
+int plume_verify_batch_sec1(plume_ctx* ctx, int version, size_t n,
+                            const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                            const uint8_t* pk33, const uint8_t* nullifier33, const uint8_t* c, const uint8_t* s,
+                            const uint8_t* r_point33, const uint8_t* hashed_to_curve_r33, uint8_t* ok);
+
 /* Device-pointer variants: all pointers are device memory of the context's GPU, `stream` is a
  * cudaStream_t (passed as void* to keep CUDA headers out of this file).  n must not exceed
  * plume_ctx_chunk_items().  Work is enqueued; the caller synchronises the stream. */
@@ -135,7 +160,7 @@ uint64_t plume_ctx_launch_count(const plume_ctx* ctx);
  * plume_ctx_stage_ms returns the summed duration in milliseconds of all launches of the named
  * stage since profiling was switched on (and their number in *launches), synchronising the
  * context's streams first.  Stage names: "sign_fixed", "sign_h2c", "sign_varbase", "sign_final",
- * "verify_h2c", "verify_muls", "verify_final", "h2c_map", "h2c_out", "binv".
+ * "verify_h2c", "verify_muls", "verify_final", "h2c_map", "h2c_out", "binv", "sec1_compress", "sec1_decompress".
  * Returns a negative value for an unknown stage.  set_profiling(ctx, 1) also resets the sums. */
 int plume_ctx_set_profiling(plume_ctx* ctx, int on);
 double plume_ctx_stage_ms(plume_ctx* ctx, const char* stage, uint64_t* launches);

@@ -110,3 +110,15 @@ def sha256(msg):
     out = (ctypes.c_uint8 * 32)()
     lib().plume_oracle_sha256(bytes(msg), ctypes.c_size_t(len(msg)), out)
     return bytes(out)
+
+
+def compress33(p64):
+    out = (ctypes.c_uint8 * 33)()
+    lib().plume_oracle_compress33(bytes(p64), out)
+    return bytes(out)
+
+
+def decompress33(b33):
+    out = (ctypes.c_uint8 * 64)()
+    ok = lib().plume_oracle_decompress33(bytes(b33), out)
+    return bytes(out), int(ok)

@@ -660,6 +660,34 @@ size_t plume_oracle_encode_pt(const uint8_t* p64, uint8_t* out33) {
     point_from_wire(&p, p64);
     return encode_pt(out33, &p);
 }
+/* SEC1-compressed 33-byte slot (identity: 00 + 32 zero bytes) <-> 64-byte wire point; decoding follows k256's
+ * AffinePoint::from_encoded_point: prefix 02/03, x < p, x^3 + 7 must be a square.  Returns 1 when accepted. */
+void plume_oracle_compress33(const uint8_t* p64, uint8_t* out33) {
+    aff p;
+    memset(out33, 0, 33);
+    static const uint8_t zero[64] = {0};
+    if (memcmp(p64, zero, 64) == 0) return;
+    from_be32(p.x.v, p64); from_be32(p.y.v, p64 + 32); p.inf = 0;
+    encode_pt(out33, &p);
+}
+int plume_oracle_decompress33(const uint8_t* in33, uint8_t* out64) {
+    memset(out64, 0, 64);
+    if (in33[0] == 0) {
+        for (int i = 1; i < 33; i++) if (in33[i]) return 0;
+        return 1;
+    }
+    if (in33[0] != 2 && in33[0] != 3) return 0;
+    uint64_t x[4];
+    from_be32(x, in33 + 1);
+    if (ge4(x, P)) return 0;
+    fe fx, rhs, y, seven;
+    memcpy(fx.v, x, 32);
+    fe_sqr(&rhs, &fx); fe_mul(&rhs, &rhs, &fx); fe_set_u64(&seven, 7); fe_add(&rhs, &rhs, &seven);
+    if (!fe_sqrt(&y, &rhs)) return 0;
+    if (fe_is_odd(&y) != (in33[0] & 1)) fe_neg(&y, &y);
+    fe_to_be(out64, &fx); fe_to_be(out64 + 32, &y);
+    return 1;
+}
 void plume_oracle_expand_message_xmd(const uint8_t* msg, size_t len, size_t n, uint8_t* out) {
     expand_message_xmd(out, n, msg, len, msg, 0);
 }

@@ -251,3 +251,25 @@ def verify(version, msg, pk, nul, c, s, r_point=None, hashed_to_curve_r=None):
     else:
         d = c_sha256_vec_signal([nul, rp, zp])                  # :138-143
     return c == int.from_bytes(d, "big") % N                    # Scalar::reduce
+
+
+def compress33(p):
+    """33-byte SEC1 slot: 02/03 || x, identity = 00 followed by zeros."""
+    return bytes(33) if p is INF else encode_pt(p)
+
+
+def decompress33(b):
+    """-> (point or INF, ok) with k256's acceptance rule: prefix 02/03, x < p, x^3 + 7 a square."""
+    b = bytes(b)
+    if b[0] == 0:
+        return INF, all(v == 0 for v in b[1:])
+    x = int.from_bytes(b[1:], "big")
+    if b[0] not in (2, 3) or x >= P:
+        return INF, False
+    rhs = (x * x * x + 7) % P
+    if not is_square(rhs):
+        return INF, False
+    y = sqrt(rhs)
+    if (y & 1) != (b[0] & 1):
+        y = P - y
+    return (x, y), True

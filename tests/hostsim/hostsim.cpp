@@ -159,6 +159,11 @@ int hs_h2c_batch(uint32_t n, const uint8_t* msgs, const uint64_t* offs, uint32_t
     return 0;
 }
 
+void hs_sec1_roundtrip(uint32_t n, const uint8_t* in33, uint8_t* out64, uint8_t* ok, uint8_t* back33) {
+    for (uint32_t i = 0; i < n; i++) sec1_decompress_body(i, in33, out64, ok);
+    for (uint32_t i = 0; i < n; i++) sec1_compress_body(i, out64, back33);
+}
+
 // SSWU + isogeny of one field element (canonical LE limbs) -> affine BE 64 bytes
 void hs_map_to_curve(const uint32_t* u, uint8_t* out64) {
     fe x; memcpy(x.v, u, 32);

@@ -257,3 +257,56 @@ def test_cpp_host_mirror(golden, tmp_path):
     assert out[0] == "v1 %s %s 1 1" % (k["v1_c"]["hex"], k["v1_s"]["hex"])
     assert out[1] == "v2 %s %s 1 0" % (k["v2_c"]["hex"], k["v2_s"]["hex"])
     assert out[2] == "tampered 0" and out[3] == "zero-sk rejected" and out[4] == "batch 1000"
+
+
+def test_sec1_compressed_api(gpu_ctx):
+    """33-byte SEC1 slots in and out (compress / decompress / sign_sec1 / verify_sec1) against the
+    oracles: encodings of k*G from the reference's table, random and malformed slots, and a sign->verify round trip."""
+    import c_oracle
+    import plume_ref as R
+    rnd = random.Random(31)
+    rng = np.random.default_rng(31)
+    # decompress: valid points, identity, random x (half off-curve), non-canonical x, bad prefixes
+    slots = [R.compress33(R.pt_mul(R.G, k)) for k in range(0, 40)]
+    slots += [bytes([rnd.choice([2, 3])]) + rnd.randrange(P).to_bytes(32, "big") for _ in range(400)]
+    slots += [b"\x02" + P.to_bytes(32, "big"), b"\x03" + (2**256 - 1).to_bytes(32, "big"), b"\x04" + slots[1][1:],
+              b"\x00" + b"\x01" + bytes(31), b"\x01" + bytes(32), b"\xff" * 33]
+    blob = np.frombuffer(b"".join(slots), dtype=np.uint8)
+    pts, ok = gpu_ctx.points_decompress(blob)
+    for i, b in enumerate(slots):
+        want, good = c_oracle.decompress33(b)
+        assert int(ok[i]) == good and bytes(pts[i]) == want, i
+    good = np.flatnonzero(ok)
+    back = gpu_ctx.points_compress(np.ascontiguousarray(pts[good]))
+    for j, i in enumerate(good):
+        assert bytes(back[j]) == slots[i]
+    # sign with compressed outputs == compress(sign outputs); verify on compressed inputs
+    n = 3000
+    msgs = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    sk, r = _rand_scalars(rng, n), _rand_scalars(rng, n)
+    for ver in (1, 2):
+        o64 = gpu_ctx.sign_batch(ver, msgs, sk, r)
+        o33 = gpu_ctx.sign_batch_sec1(ver, msgs, sk, r)
+        assert np.array_equal(o33["status"], o64["status"]) and np.array_equal(o33["c"], o64["c"]) and np.array_equal(o33["s"], o64["s"])
+        for k in ("pk", "nullifier", "r_point", "hashed_to_curve_r"):
+            for i in range(0, n, 97):
+                assert bytes(o33[k][i]) == c_oracle.compress33(bytes(o64[k][i])), (k, i)
+        ok = gpu_ctx.verify_batch_sec1(ver, msgs, o33["pk"], o33["nullifier"], o33["c"], o33["s"], o33["r_point"], o33["hashed_to_curve_r"])
+        assert ok.all()
+        t = {k: o33[k].copy() for k in ("pk", "nullifier", "r_point", "hashed_to_curve_r")}
+        t["pk"][0::4, 0] ^= 1                      # wrong parity: decodes to -pk
+        t["nullifier"][1::4, 5] ^= 0x40            # different x (may or may not be on the curve)
+        t["r_point"][2::4, 0] = 7                  # bad prefix
+        ok = gpu_ctx.verify_batch_sec1(ver, msgs, t["pk"], t["nullifier"], o33["c"], o33["s"], t["r_point"], t["hashed_to_curve_r"])
+        # oracle: decode each slot, then verify
+        for i in list(range(0, 40)) + list(range(n - 40, n)):
+            dec = [c_oracle.decompress33(bytes(t[k][i])) for k in ("pk", "nullifier", "r_point", "hashed_to_curve_r")]
+            use = dec if ver == 1 else dec[:2]
+            want = 0
+            if all(g for _, g in use):
+                want = int(c_oracle.verify_batch(ver, msgs[i:i + 1], dec[0][0], dec[1][0], o33["c"][i:i + 1], o33["s"][i:i + 1],
+                                                 dec[2][0], dec[3][0])[0])
+            assert int(ok[i]) == want, (ver, i)
+        assert ok[3::4].all() and not ok[0::4].any()
+        if ver == 1:
+            assert not ok[2::4].any()

@@ -181,3 +181,29 @@ def test_verify_identity_points():
     assert R.verify(2, msg, None, None, c, s)
     assert c_oracle.verify_batch(2, [msg], z, z, cb, sb)[0] == 1
     assert H.verify_batch(2, [msg], z, z, cb, sb, z, z)[0] == 1
+
+
+def test_sec1_compressed_points():
+    """33-byte slots <-> affine points, device code (host-sim) vs both oracles."""
+    rnd = random.Random(9)
+    slots, want = [], []
+    pts = [R.pt_mul(R.G, rnd.randrange(1, N)) for _ in range(12)] + [None]
+    for p in pts:
+        slots.append(R.compress33(p))
+    for _ in range(20):       # random x: about half are not on the curve
+        slots.append(bytes([rnd.choice([2, 3])]) + rnd.randrange(P).to_bytes(32, "big"))
+    slots.append(b"\x02" + P.to_bytes(32, "big"))                      # x = p: non-canonical
+    slots.append(b"\x03" + (2**256 - 1).to_bytes(32, "big"))
+    slots.append(b"\x04" + slots[0][1:])                               # bad prefix
+    slots.append(b"\x00" + b"\x01" + bytes(31))                        # identity prefix with junk
+    n = len(slots)
+    blob = np.frombuffer(b"".join(slots), dtype=np.uint8).copy()
+    out64 = np.zeros((n, 64), dtype=np.uint8); ok = np.zeros(n, dtype=np.uint8); back = np.zeros((n, 33), dtype=np.uint8)
+    H.lib().hs_sec1_roundtrip(n, H._p(blob), H._p(out64), H._p(ok), H._p(back))
+    for i, b in enumerate(slots):
+        p, good = R.decompress33(b)
+        o64, g2 = c_oracle.decompress33(b)
+        assert bool(ok[i]) == bool(good) == bool(g2), i
+        assert bytes(out64[i]) == _pt64(p) == o64, i
+        if good:
+            assert bytes(back[i]) == b == c_oracle.compress33(o64)

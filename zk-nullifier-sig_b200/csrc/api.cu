@@ -15,9 +15,9 @@
 namespace {
 
 const char* const kStageNames[] = {"sign_fixed", "sign_h2c", "sign_varbase", "sign_final", "verify_h2c",
-                                   "verify_muls", "verify_final", "h2c_map", "h2c_out", "binv"};
+                                   "verify_muls", "verify_final", "h2c_map", "h2c_out", "binv", "sec1_compress", "sec1_decompress"};
 enum Stage { ST_SIGN_FIXED, ST_SIGN_H2C, ST_SIGN_VARBASE, ST_SIGN_FINAL, ST_VERIFY_H2C, ST_VERIFY_MULS,
-             ST_VERIFY_FINAL, ST_H2C_MAP, ST_H2C_OUT, ST_BINV, ST_COUNT };
+             ST_VERIFY_FINAL, ST_H2C_MAP, ST_H2C_OUT, ST_BINV, ST_SEC1_COMPRESS, ST_SEC1_DECOMPRESS, ST_COUNT };
 
 struct PendingCopy { void* dst; const void* src; size_t bytes; };
 
@@ -544,6 +544,175 @@ int plume_hash_to_curve_batch(plume_ctx* ctx, size_t n, const uint8_t* msgs, con
         a.ws = L.ws;
         if (int rc = enqueue_h2c(ctx, a, L.stream)) return rc;
         if (int rc = lane_fetch(ctx, L, out + i0 * 64, o_out, cn * 64)) return rc;
+    }
+    for (Lane& L : ctx->lanes) if (int rc = lane_finish(ctx, L)) return rc;
+    return PLUME_OK;
+}
+
+int plume_points_compress_batch_device(plume_ctx* ctx, size_t n, const uint8_t* in64, uint8_t* out33, void* stream) {
+    if (!ctx || !in64 || !out33) return PLUME_E_ARG;
+    if (n == 0) return PLUME_OK;
+    ScopedDevice sd(ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    RUN(ST_SEC1_COMPRESS, launch_sec1_compress((uint32_t)n, in64, out33, s));
+    return PLUME_OK;
+}
+int plume_points_decompress_batch_device(plume_ctx* ctx, size_t n, const uint8_t* in33, uint8_t* out64, uint8_t* ok, void* stream) {
+    if (!ctx || !in33 || !out64 || !ok) return PLUME_E_ARG;
+    if (n == 0) return PLUME_OK;
+    ScopedDevice sd(ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    RUN(ST_SEC1_DECOMPRESS, launch_sec1_decompress((uint32_t)n, in33, out64, ok, s));
+    return PLUME_OK;
+}
+
+// ---- SEC1-compressed wire form (33-byte slots) -------------------------------------------------------------------
+int plume_points_compress_batch(plume_ctx* ctx, size_t n, const uint8_t* in64, uint8_t* out33) {
+    if (!ctx) return PLUME_E_ARG;
+    if (n == 0) return PLUME_OK;
+    if (!in64 || !out33) return fail(ctx, PLUME_E_ARG, "null array");
+    ScopedDevice sd(ctx->device);
+    size_t k = 0;
+    for (size_t i0 = 0; i0 < n; i0 += ctx->chunk, k++) {
+        const size_t cn = (n - i0 < ctx->chunk) ? n - i0 : ctx->chunk;
+        Lane& L = ctx->lanes[k & 1];
+        if (int rc = lane_finish(ctx, L)) return rc;
+        if (int rc = lane_reserve(ctx, L, cn * 97 + 4096)) return rc;
+        L.d_io_used = 0;
+        L.busy = true;
+        uint8_t* d_in;
+        if (int rc = lane_input(ctx, L, in64 + i0 * 64, cn * 64, &d_in)) return rc;
+        size_t o_out;
+        uint8_t* d_out = lane_output(L, cn * 33, &o_out);
+        cudaStream_t s = L.stream;
+        RUN(ST_SEC1_COMPRESS, launch_sec1_compress((uint32_t)cn, d_in, d_out, s));
+        if (int rc = lane_fetch(ctx, L, out33 + i0 * 33, o_out, cn * 33)) return rc;
+    }
+    for (Lane& L : ctx->lanes) if (int rc = lane_finish(ctx, L)) return rc;
+    return PLUME_OK;
+}
+
+int plume_points_decompress_batch(plume_ctx* ctx, size_t n, const uint8_t* in33, uint8_t* out64, uint8_t* ok) {
+    if (!ctx) return PLUME_E_ARG;
+    if (n == 0) return PLUME_OK;
+    if (!in33 || !out64 || !ok) return fail(ctx, PLUME_E_ARG, "null array");
+    ScopedDevice sd(ctx->device);
+    size_t k = 0;
+    for (size_t i0 = 0; i0 < n; i0 += ctx->chunk, k++) {
+        const size_t cn = (n - i0 < ctx->chunk) ? n - i0 : ctx->chunk;
+        Lane& L = ctx->lanes[k & 1];
+        if (int rc = lane_finish(ctx, L)) return rc;
+        if (int rc = lane_reserve(ctx, L, cn * 98 + 4096)) return rc;
+        L.d_io_used = 0;
+        L.busy = true;
+        uint8_t* d_in;
+        if (int rc = lane_input(ctx, L, in33 + i0 * 33, cn * 33, &d_in)) return rc;
+        size_t o_out, o_ok;
+        uint8_t* d_out = lane_output(L, cn * 64, &o_out);
+        uint8_t* d_ok = lane_output(L, cn, &o_ok);
+        cudaStream_t s = L.stream;
+        RUN(ST_SEC1_DECOMPRESS, launch_sec1_decompress((uint32_t)cn, d_in, d_out, d_ok, s));
+        if (int rc = lane_fetch(ctx, L, out64 + i0 * 64, o_out, cn * 64)) return rc;
+        if (int rc = lane_fetch(ctx, L, ok + i0, o_ok, cn)) return rc;
+    }
+    for (Lane& L : ctx->lanes) if (int rc = lane_finish(ctx, L)) return rc;
+    return PLUME_OK;
+}
+
+int plume_sign_batch_sec1(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                          const uint8_t* sk, const uint8_t* r, uint8_t* pk33, uint8_t* nullifier33, uint8_t* c, uint8_t* s_out,
+                          uint8_t* r_point33, uint8_t* hashed_to_curve_r33, uint8_t* status) {
+    if (int rc = check_common(ctx, n, msgs, msg_offsets, msg_len)) return rc;
+    if (version != 1 && version != 2) return fail(ctx, PLUME_E_ARG, "version must be 1 or 2");
+    if (n == 0) return PLUME_OK;
+    if (!sk || !r || !pk33 || !nullifier33 || !c || !s_out || !status) return fail(ctx, PLUME_E_ARG, "null array");
+    ScopedDevice sd(ctx->device);
+    size_t k = 0;
+    for (size_t i0 = 0; i0 < n; i0 += ctx->chunk, k++) {
+        const size_t cn = (n - i0 < ctx->chunk) ? n - i0 : ctx->chunk;
+        Lane& L = ctx->lanes[k & 1];
+        if (int rc = lane_finish(ctx, L)) return rc;
+        if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * (64 + 64 * 4 + 33 * 4 + 64 + 1) + 8192)) return rc;
+        L.d_io_used = 0;
+        L.busy = true;
+        sign_args a;
+        a.version = version; a.n = (uint32_t)cn;
+        if (int rc = lane_msgs(ctx, L, msgs, msg_offsets, msg_len, i0, cn, &a.msgs)) return rc;
+        uint8_t *d_sk, *d_r;
+        if (int rc = lane_input(ctx, L, sk + i0 * 32, cn * 32, &d_sk)) return rc;
+        if (int rc = lane_input(ctx, L, r + i0 * 32, cn * 32, &d_r)) return rc;
+        a.sk = d_sk; a.r = d_r;
+        size_t o_tmp, o_c, o_s, o_st, o33[4] = {0, 0, 0, 0};
+        a.pk = lane_output(L, cn * 64, &o_tmp);
+        a.nullifier = lane_output(L, cn * 64, &o_tmp);
+        a.c = lane_output(L, cn * 32, &o_c);
+        a.s = lane_output(L, cn * 32, &o_s);
+        a.r_point = lane_output(L, cn * 64, &o_tmp);
+        a.hashed_to_curve_r = lane_output(L, cn * 64, &o_tmp);
+        a.status = lane_output(L, cn, &o_st);
+        a.ws = L.ws; a.gtab = ctx->gtab; a.gw = ctx->gw; a.vbtab = L.vbtab;
+        if (int rc = enqueue_sign(ctx, a, L.stream)) return rc;
+        cudaStream_t s = L.stream;
+        uint8_t* src[4] = {a.pk, a.nullifier, a.r_point, a.hashed_to_curve_r};
+        uint8_t* dst[4] = {pk33, nullifier33, r_point33, hashed_to_curve_r33};
+        for (int q = 0; q < 4; q++) {
+            if (!dst[q]) continue;
+            uint8_t* d33 = lane_output(L, cn * 33, &o33[q]);
+            RUN(ST_SEC1_COMPRESS, launch_sec1_compress((uint32_t)cn, src[q], d33, s));
+            if (int rc = lane_fetch(ctx, L, dst[q] + i0 * 33, o33[q], cn * 33)) return rc;
+        }
+        if (int rc = lane_fetch(ctx, L, c + i0 * 32, o_c, cn * 32)) return rc;
+        if (int rc = lane_fetch(ctx, L, s_out + i0 * 32, o_s, cn * 32)) return rc;
+        if (int rc = lane_fetch(ctx, L, status + i0, o_st, cn)) return rc;
+    }
+    for (Lane& L : ctx->lanes) if (int rc = lane_finish(ctx, L)) return rc;
+    return PLUME_OK;
+}
+
+int plume_verify_batch_sec1(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                            const uint8_t* pk33, const uint8_t* nullifier33, const uint8_t* c, const uint8_t* s_in,
+                            const uint8_t* r_point33, const uint8_t* hashed_to_curve_r33, uint8_t* ok) {
+    if (int rc = check_common(ctx, n, msgs, msg_offsets, msg_len)) return rc;
+    if (version != 1 && version != 2) return fail(ctx, PLUME_E_ARG, "version must be 1 or 2");
+    if (n == 0) return PLUME_OK;
+    if (!pk33 || !nullifier33 || !c || !s_in || !ok) return fail(ctx, PLUME_E_ARG, "null array");
+    if (version == 1 && (!r_point33 || !hashed_to_curve_r33)) return fail(ctx, PLUME_E_ARG, "V1 needs r_point and hashed_to_curve_r");
+    ScopedDevice sd(ctx->device);
+    size_t k = 0;
+    for (size_t i0 = 0; i0 < n; i0 += ctx->chunk, k++) {
+        const size_t cn = (n - i0 < ctx->chunk) ? n - i0 : ctx->chunk;
+        Lane& L = ctx->lanes[k & 1];
+        if (int rc = lane_finish(ctx, L)) return rc;
+        if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * (33 * 4 + 64 * 4 + 64 + 5) + 8192)) return rc;
+        L.d_io_used = 0;
+        L.busy = true;
+        verify_args a;
+        a.version = version; a.n = (uint32_t)cn;
+        if (int rc = lane_msgs(ctx, L, msgs, msg_offsets, msg_len, i0, cn, &a.msgs)) return rc;
+        cudaStream_t s = L.stream;
+        const uint8_t* src[4] = {pk33, nullifier33, version == 1 ? r_point33 : nullptr, version == 1 ? hashed_to_curve_r33 : nullptr};
+        uint8_t* pts[4] = {nullptr, nullptr, nullptr, nullptr};
+        uint8_t* flg[4] = {nullptr, nullptr, nullptr, nullptr};
+        for (int q = 0; q < 4; q++) {
+            if (!src[q]) continue;
+            uint8_t* d33;
+            if (int rc = lane_input(ctx, L, src[q] + i0 * 33, cn * 33, &d33)) return rc;
+            size_t o_tmp;
+            pts[q] = lane_output(L, cn * 64, &o_tmp);
+            flg[q] = lane_output(L, cn, &o_tmp);
+            RUN(ST_SEC1_DECOMPRESS, launch_sec1_decompress((uint32_t)cn, d33, pts[q], flg[q], s));
+        }
+        uint8_t *d_c, *d_s;
+        if (int rc = lane_input(ctx, L, c + i0 * 32, cn * 32, &d_c)) return rc;
+        if (int rc = lane_input(ctx, L, s_in + i0 * 32, cn * 32, &d_s)) return rc;
+        a.pk = pts[0]; a.nullifier = pts[1]; a.c = d_c; a.s = d_s; a.r_point = pts[2]; a.hashed_to_curve_r = pts[3];
+        size_t o_ok;
+        a.ok = lane_output(L, cn, &o_ok);
+        a.ws = L.ws; a.gtab = ctx->gtab; a.gw = ctx->gw; a.vbtab = L.vbtab;
+        if (int rc = enqueue_verify(ctx, a, L.stream)) return rc;
+        CU(launch_and_flags((uint32_t)cn, a.ok, flg[0], flg[1], flg[2], flg[3], s));
+        ctx->launches++;
+        if (int rc = lane_fetch(ctx, L, ok + i0, o_ok, cn)) return rc;
     }
     for (Lane& L : ctx->lanes) if (int rc = lane_finish(ctx, L)) return rc;
     return PLUME_OK;

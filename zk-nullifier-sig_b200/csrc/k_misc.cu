@@ -25,6 +25,18 @@ __global__ void __launch_bounds__(128) k_gtab_norm(uint32_t ne, uint32_t* tab, c
     if (e < ne) gtab_norm_body(e, tab, zs);
 }
 
+__global__ void __launch_bounds__(128) k_sec1_compress(uint32_t n, const uint8_t* in64, uint8_t* out33) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sec1_compress_body(i, in64, out33);
+}
+__global__ void __launch_bounds__(128, 4) k_sec1_decompress(uint32_t n, const uint8_t* in33, uint8_t* out64, uint8_t* ok) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sec1_decompress_body(i, in33, out64, ok);
+}
+__global__ void k_and_flags(uint32_t n, uint8_t* ok, const uint8_t* f0, const uint8_t* f1, const uint8_t* f2, const uint8_t* f3) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) and_flags_body(i, ok, f0, f1, f2, f3);
+}
 // element-wise field operation on raw little-endian limb arrays (test hook: plume_debug_fe_op)
 __global__ void __launch_bounds__(128) k_debug_fe_op(int op, uint32_t n, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -97,6 +109,18 @@ cudaError_t launch_gtab_entries(uint32_t ne, uint32_t* tab, uint32_t* zs, const 
 }
 cudaError_t launch_gtab_norm(uint32_t ne, uint32_t* tab, const uint32_t* zs, cudaStream_t s) {
     k_gtab_norm<<<grid_for(ne, 128), 128, 0, s>>>(ne, tab, zs);
+    return cudaGetLastError();
+}
+cudaError_t launch_sec1_compress(uint32_t n, const uint8_t* in64, uint8_t* out33, cudaStream_t s) {
+    k_sec1_compress<<<grid_for(n, 128), 128, 0, s>>>(n, in64, out33);
+    return cudaGetLastError();
+}
+cudaError_t launch_sec1_decompress(uint32_t n, const uint8_t* in33, uint8_t* out64, uint8_t* ok, cudaStream_t s) {
+    k_sec1_decompress<<<grid_for(n, 128), 128, 0, s>>>(n, in33, out64, ok);
+    return cudaGetLastError();
+}
+cudaError_t launch_and_flags(uint32_t n, uint8_t* ok, const uint8_t* f0, const uint8_t* f1, const uint8_t* f2, const uint8_t* f3, cudaStream_t s) {
+    k_and_flags<<<grid_for(n, 256), 256, 0, s>>>(n, ok, f0, f1, f2, f3);
     return cudaGetLastError();
 }
 cudaError_t launch_debug_fe_op(int op, uint32_t n, const uint32_t* a, const uint32_t* b, uint32_t* out, cudaStream_t s) {

@@ -474,6 +474,63 @@ PLUME_DEV void h2c_stage_out(uint32_t i, const h2c_args& a) {
     st_point_be(a.out + (size_t)i * 64, h);
 }
 
+// ---- SEC1-compressed wire form (the form the JS binding exchanges, javascript/src/lib.rs:97-117) ----
+// 33-byte slots: 02/03 || x for a finite point, 00 followed by 32 zero bytes for the identity.
+PLUME_DEV void sec1_compress_body(uint32_t i, const uint8_t* in64, uint8_t* out33) {
+    aff p;
+    p.x = ld_fe_be(in64 + (size_t)i * 64);
+    p.y = ld_fe_be(in64 + (size_t)i * 64 + 32);
+    uint32_t o = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) o |= p.x.v[k] | p.y.v[k];
+    p.inf = (o == 0);
+    uint8_t e[33];
+    uint32_t len = enc_point33(e, p);
+    uint8_t* dst = out33 + (size_t)i * 33;
+#pragma unroll 1
+    for (uint32_t k = 0; k < 33; k++) dst[k] = k < len ? e[k] : 0;
+}
+// ok = 1 and out = x || y when the slot decodes the way k256's AffinePoint::from_encoded_point accepts it
+// (prefix 02/03, x < p, x^3 + 7 a square); ok = 1 and out = 0 for the identity slot; ok = 0, out = 0 otherwise.
+PLUME_DEV void sec1_decompress_body(uint32_t i, const uint8_t* in33, uint8_t* out64, uint8_t* ok) {
+    const uint8_t* src = in33 + (size_t)i * 33;
+    uint8_t prefix = src[0];
+    uint32_t w[8];
+    uint32_t any = 0;
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) {
+        w[k] = ((uint32_t)src[1 + 4 * k] << 24) | ((uint32_t)src[2 + 4 * k] << 16) | ((uint32_t)src[3 + 4 * k] << 8) | src[4 + 4 * k];
+        any |= w[k];
+    }
+    fe x;
+#pragma unroll
+    for (int k = 0; k < 8; k++) x.v[k] = w[7 - k];
+    aff p = aff_infinity();
+    bool good = false;
+    if (prefix == 0) {
+        good = (any == 0);
+    } else if ((prefix == 2 || prefix == 3) && !fe_ge_p(x)) {
+        fe rhs = fe_add(fe_mul(fe_sqr(x), x), fe_set_u32(7));
+        fe y = fe_norm(fe_sqrt_cand(rhs));
+        if (fe_eq(fe_sqr(y), rhs)) {
+            if ((y.v[0] & 1) != (uint32_t)(prefix & 1)) y = fe_norm(fe_neg(y));
+            p.x = x; p.y = y; p.inf = 0;
+            good = true;
+        }
+    }
+    st_point_be(out64 + (size_t)i * 64, p);
+    ok[i] = good ? 1 : 0;
+}
+// ok[i] &= f0[i] & f1[i] & f2[i] & f3[i]   (null pointers are skipped)
+PLUME_DEV void and_flags_body(uint32_t i, uint8_t* ok, const uint8_t* f0, const uint8_t* f1, const uint8_t* f2, const uint8_t* f3) {
+    uint8_t v = ok[i];
+    if (f0) v &= f0[i];
+    if (f1) v &= f1[i];
+    if (f2) v &= f2[i];
+    if (f3) v &= f3[i];
+    ok[i] = v;
+}
+
 // ---- generator table construction (once per context) -------------------------------------------------------
 // bases[j] = 2^(w*j) * G, affine, 16 words each
 PLUME_DEV void gtab_bases_body(uint32_t* bases, int w) {

@@ -158,6 +158,50 @@ class PlumeContext:
         self._check(rc, "plume_verify_batch")
         return ok
 
+    # ---- SEC1-compressed wire form (33-byte slots) ----------------------------------------------------
+    def points_compress(self, pts64):
+        a = _as_u8(pts64); n = a.size // 64; a = a.reshape(n, 64)
+        out = np.empty((n, 33), dtype=np.uint8)
+        self._check(self._lib.plume_points_compress_batch(self._h, n, _ptr(a), _ptr(out)), "plume_points_compress_batch")
+        return out
+
+    def points_decompress(self, pts33):
+        a = _as_u8(pts33); n = a.size // 33; a = a.reshape(n, 33)
+        out = np.empty((n, 64), dtype=np.uint8); ok = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.plume_points_decompress_batch(self._h, n, _ptr(a), _ptr(out), _ptr(ok)), "plume_points_decompress_batch")
+        return out, ok
+
+    def points_compress_device(self, n, in64, out33, stream=0):
+        vp = ctypes.c_void_p
+        self._check(self._lib.plume_points_compress_batch_device(self._h, n, vp(in64), vp(out33), vp(stream or None)), "plume_points_compress_batch_device")
+
+    def points_decompress_device(self, n, in33, out64, ok, stream=0):
+        vp = ctypes.c_void_p
+        self._check(self._lib.plume_points_decompress_batch_device(self._h, n, vp(in33), vp(out64), vp(ok), vp(stream or None)), "plume_points_decompress_batch_device")
+
+    def sign_batch_sec1(self, version, msgs, sk, r):
+        blob, offs, mlen, n = self._msgs(msgs, None)
+        sk = _as_u8(sk, (n, 32)); r = _as_u8(r, (n, 32))
+        o = {k: np.empty((n, w), dtype=np.uint8) for k, w in
+             (("pk", 33), ("nullifier", 33), ("c", 32), ("s", 32), ("r_point", 33), ("hashed_to_curve_r", 33))}
+        o["status"] = np.empty(n, dtype=np.uint8)
+        rc = self._lib.plume_sign_batch_sec1(self._h, version, n, _ptr(blob), _ptr(offs), mlen, _ptr(sk), _ptr(r), _ptr(o["pk"]),
+                                             _ptr(o["nullifier"]), _ptr(o["c"]), _ptr(o["s"]), _ptr(o["r_point"]),
+                                             _ptr(o["hashed_to_curve_r"]), _ptr(o["status"]))
+        self._check(rc, "plume_sign_batch_sec1")
+        return o
+
+    def verify_batch_sec1(self, version, msgs, pk33, nullifier33, c, s, r_point33=None, hashed_to_curve_r33=None):
+        blob, offs, mlen, n = self._msgs(msgs, None)
+        pk = _as_u8(pk33, (n, 33)); nul = _as_u8(nullifier33, (n, 33)); c = _as_u8(c, (n, 32)); s = _as_u8(s, (n, 32))
+        rp = None if r_point33 is None else _as_u8(r_point33, (n, 33))
+        hr = None if hashed_to_curve_r33 is None else _as_u8(hashed_to_curve_r33, (n, 33))
+        ok = np.empty(n, dtype=np.uint8)
+        rc = self._lib.plume_verify_batch_sec1(self._h, version, n, _ptr(blob), _ptr(offs), mlen, _ptr(pk), _ptr(nul), _ptr(c),
+                                               _ptr(s), _ptr(rp), _ptr(hr), _ptr(ok))
+        self._check(rc, "plume_verify_batch_sec1")
+        return ok
+
     # ---- device-pointer entry points (raw addresses, e.g. torch tensors' data_ptr()) -----------------
     def sign_batch_device(self, version, n, msgs, msg_offsets, msg_len, sk, r, pk, nullifier, c, s,
                           r_point, hashed_to_curve_r, status, stream=0):
@@ -189,6 +233,18 @@ class PlumeContext:
                                         vp(nullifier), vp(c), vp(s), vp(r_point or None), vp(hashed_to_curve_r or None),
                                         vp(status))
         self._check(rc, "plume_sign_batch")
+
+    def sign_batch_sec1_ptr(self, version, n, msgs, msg_offsets, msg_len, sk, r, pk, nullifier, c, s, r_point, hashed_to_curve_r, status):
+        vp = ctypes.c_void_p
+        rc = self._lib.plume_sign_batch_sec1(self._h, version, n, vp(msgs), vp(msg_offsets or None), msg_len, vp(sk), vp(r), vp(pk),
+                                             vp(nullifier), vp(c), vp(s), vp(r_point or None), vp(hashed_to_curve_r or None), vp(status))
+        self._check(rc, "plume_sign_batch_sec1")
+
+    def verify_batch_sec1_ptr(self, version, n, msgs, msg_offsets, msg_len, pk, nullifier, c, s, r_point, hashed_to_curve_r, ok):
+        vp = ctypes.c_void_p
+        rc = self._lib.plume_verify_batch_sec1(self._h, version, n, vp(msgs), vp(msg_offsets or None), msg_len, vp(pk), vp(nullifier),
+                                               vp(c), vp(s), vp(r_point or None), vp(hashed_to_curve_r or None), vp(ok))
+        self._check(rc, "plume_verify_batch_sec1")
 
     def verify_batch_ptr(self, version, n, msgs, msg_offsets, msg_len, pk, nullifier, c, s, r_point, hashed_to_curve_r, ok):
         vp = ctypes.c_void_p
