@@ -328,7 +328,7 @@ def main():
     launches = ctx.launch_count - launches0
     stage = {}
     for st in ("sign_fixed", "sign_h2c", "sign_varbase", "sign_final", "verify_h2c", "verify_muls", "verify_final", "h2c_map",
-               "h2c_out", "binv"):
+               "h2c_out", "binv", "sec1_compress", "sec1_decompress"):
         ms, k = ctx.stage_ms(st)
         if k:
             stage[st] = {"ms_total": round(ms, 3), "launches": k}
