@@ -165,10 +165,13 @@ uint64_t plume_ctx_launch_count(const plume_ctx* ctx);
 int plume_ctx_set_profiling(plume_ctx* ctx, int on);
 double plume_ctx_stage_ms(plume_ctx* ctx, const char* stage, uint64_t* launches);
 
-/* Integer-pipe microbenchmark: runs `iters` rounds of independent IMAD.WIDE.U32 chains on every SM
- * and returns the measured 32x32->64 multiply-add rate (limb products per second), the
- * denominator of the integer-ALU roofline (SURVEY.md section 8d "Peak"). */
+/* Integer-pipe microbenchmark, the denominator of the integer-ALU roofline (SURVEY.md section 8d "Peak"):
+ * the sustained rate of 32x32->64-bit multiply-accumulates (limb products per second) over every SM, in two
+ * forms -- plain IMAD.WIDE.U32 with a 64-bit addend, and the carry-chain form (IMAD.WIDE.U32.X rows fused from
+ * mad.lo.cc / madc.hi.cc) the shipped multiplier is built from.  plume_measure_imad_peak returns the faster
+ * of the two; plume_measure_imad_rates returns both (either pointer may be NULL). */
 int plume_measure_imad_peak(plume_ctx* ctx, int iters, double* limb_products_per_s);
+int plume_measure_imad_rates(plume_ctx* ctx, int iters, double* plain_limb_products_per_s, double* carry_limb_products_per_s);
 
 /* Test hook: element-wise base-field operation on raw limb arrays (n x 8 little-endian 32-bit limbs,
  * any representative below 2^256; host pointers).  op: 0 a*b, 1 a^2, 2 a+b, 3 a-b, 4 1/a, 5 canonical(a),

@@ -139,6 +139,183 @@ __global__ void kG(uint32_t* sink) {
     if (t == 0x1234567) sink[0] = t;
 }
 
+
+// H: DFMA (fma.rz.f64), 16 independent accumulators
+__global__ void kH(uint32_t* sink) {
+    double x = 1.0 + threadIdx.x * 1e-9, y = 1.0 - threadIdx.x * 1e-9;
+    double a[16];
+    for (int i = 0; i < 16; i++) a[i] = x + i;
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+#pragma unroll
+            for (int i = 0; i < 16; i++) asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(a[i]) : "d"(x), "d"(y));
+    }
+    double t = 0;
+    for (int i = 0; i < 16; i++) t += a[i];
+    if (t == 0.12345) sink[0] = 1;
+}
+// I: 16 DFMA + 16 plain IMAD.WIDE interleaved (do the FP64 and FMA-heavy pipes overlap?)
+__global__ void kI(uint32_t* sink) {
+    double x = 1.0 + threadIdx.x * 1e-9, y = 1.0 - threadIdx.x * 1e-9;
+    uint32_t xi = threadIdx.x * 2654435761u + 1, yi = xi ^ 0x9E3779B9u;
+    double a[16];
+    unsigned long long b[16];
+    for (int i = 0; i < 16; i++) { a[i] = x + i; b[i] = xi + i; }
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(a[i]) : "d"(x), "d"(y));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(b[i]) : "r"(xi), "r"(yi));
+        }
+    }
+    double t = 0; unsigned long long tb = 0;
+    for (int i = 0; i < 16; i++) { t += a[i]; tb ^= b[i]; }
+    if (t == 0.12345 || tb == 0x1234567) sink[0] = 1;
+}
+// J: 16 plain IMAD.WIDE + 16 plain IADD3 (no carry) interleaved
+__global__ void kJ(uint32_t* sink) {
+    uint32_t xi = threadIdx.x * 2654435761u + 1, yi = xi ^ 0x9E3779B9u;
+    unsigned long long b[16];
+    uint32_t s[16];
+    for (int i = 0; i < 16; i++) { b[i] = xi + i; s[i] = yi + i; }
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(b[i]) : "r"(xi), "r"(yi));
+            asm volatile("add.u32 %0, %0, %1;" : "+r"(s[i]) : "r"(xi));
+        }
+    }
+    unsigned long long tb = 0;
+    for (int i = 0; i < 16; i++) { tb ^= b[i]; tb ^= s[i]; }
+    if (tb == 0x1234567) sink[0] = 1;
+}
+// K: 16 plain IMAD.WIDE + 16 SHF (funnel shift) + 16 LOP3 interleaved
+__global__ void kK(uint32_t* sink) {
+    uint32_t xi = threadIdx.x * 2654435761u + 1, yi = xi ^ 0x9E3779B9u;
+    unsigned long long b[16];
+    uint32_t s[16], q[16];
+    for (int i = 0; i < 16; i++) { b[i] = xi + i; s[i] = yi + i; q[i] = yi * i; }
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(b[i]) : "r"(xi), "r"(yi));
+            asm volatile("shf.r.wrap.b32 %0, %0, %1, 29;" : "+r"(s[i]) : "r"(xi));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(q[i]) : "r"(xi), "r"(yi));
+        }
+    }
+    unsigned long long tb = 0;
+    for (int i = 0; i < 16; i++) { tb ^= b[i]; tb ^= s[i]; tb ^= q[i]; }
+    if (tb == 0x1234567) sink[0] = 1;
+}
+// L: plain IADD3 (no carry), 32 independent
+__global__ void kL(uint32_t* sink) {
+    uint32_t xi = threadIdx.x * 2654435761u + 1;
+    uint32_t s[32];
+    for (int i = 0; i < 32; i++) s[i] = xi + i;
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 32; i++) asm volatile("add.u32 %0, %0, %1;" : "+r"(s[i]) : "r"(xi));
+    }
+    uint32_t t = 0;
+    for (int i = 0; i < 32; i++) t ^= s[i];
+    if (t == 0x1234567) sink[0] = 1;
+}
+// M: 16 DFMA + 16 IADD3 pairs (64-bit integer add of the bit patterns, add.cc/addc)
+__global__ void kM(uint32_t* sink) {
+    double x = 1.0 + threadIdx.x * 1e-9, y = 1.0 - threadIdx.x * 1e-9;
+    uint32_t xi = threadIdx.x * 2654435761u + 1;
+    double a[16];
+    uint32_t lo[16], hi[16];
+    for (int i = 0; i < 16; i++) { a[i] = x + i; lo[i] = xi + i; hi[i] = xi * i; }
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(a[i]) : "d"(x), "d"(y));
+            asm volatile("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %2;" : "+r"(lo[i]), "+r"(hi[i]) : "r"(xi));
+        }
+    }
+    double t = 0; uint32_t tb = 0;
+    for (int i = 0; i < 16; i++) { t += a[i]; tb ^= lo[i] ^ hi[i]; }
+    if (t == 0.12345 || tb == 0x1234567) sink[0] = 1;
+}
+// N: all three: 16 DFMA + 16 IMAD.WIDE + 16 IADD3
+__global__ void kN(uint32_t* sink) {
+    double x = 1.0 + threadIdx.x * 1e-9, y = 1.0 - threadIdx.x * 1e-9;
+    uint32_t xi = threadIdx.x * 2654435761u + 1, yi = xi ^ 0x9E3779B9u;
+    double a[16];
+    unsigned long long b[16];
+    uint32_t s[16];
+    for (int i = 0; i < 16; i++) { a[i] = x + i; b[i] = xi + i; s[i] = yi + i; }
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(a[i]) : "d"(x), "d"(y));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(b[i]) : "r"(xi), "r"(yi));
+            asm volatile("add.u32 %0, %0, %1;" : "+r"(s[i]) : "r"(xi));
+        }
+    }
+    double t = 0; unsigned long long tb = 0;
+    for (int i = 0; i < 16; i++) { t += a[i]; tb ^= b[i] ^ s[i]; }
+    if (t == 0.12345 || tb == 0x1234567) sink[0] = 1;
+}
+// O: 64-bit add pairs alone (add.cc + addc), 16 independent pairs
+__global__ void kO(uint32_t* sink) {
+    uint32_t xi = threadIdx.x * 2654435761u + 1;
+    uint32_t lo[16], hi[16];
+    for (int i = 0; i < 16; i++) { lo[i] = xi + i; hi[i] = xi * i; }
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            asm volatile("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %2;" : "+r"(lo[i]), "+r"(hi[i]) : "r"(xi));
+    }
+    uint32_t tb = 0;
+    for (int i = 0; i < 16; i++) tb ^= lo[i] ^ hi[i];
+    if (tb == 0x1234567) sink[0] = 1;
+}
+// P: native 64-bit integer add (add.u64), 16 independent
+__global__ void kP(uint32_t* sink) {
+    unsigned long long xi = threadIdx.x * 2654435761ull + 1;
+    unsigned long long s[16];
+    for (int i = 0; i < 16; i++) s[i] = xi * (i + 3);
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+#pragma unroll
+        for (int i = 0; i < 16; i++) asm volatile("add.u64 %0, %0, %1;" : "+l"(s[i]) : "l"(xi));
+    }
+    unsigned long long tb = 0;
+    for (int i = 0; i < 16; i++) tb ^= s[i];
+    if (tb == 0x1234567) sink[0] = 1;
+}
+// Q: DADD alone (add.rz.f64), 16 independent
+__global__ void kQ(uint32_t* sink) {
+    double x = 1.0 + threadIdx.x * 1e-9;
+    double a[16];
+    for (int i = 0; i < 16; i++) a[i] = x + i;
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+#pragma unroll
+            for (int i = 0; i < 16; i++) asm volatile("add.rz.f64 %0, %0, %1;" : "+d"(a[i]) : "d"(x));
+    }
+    double t = 0;
+    for (int i = 0; i < 16; i++) t += a[i];
+    if (t == 0.12345) sink[0] = 1;
+}
+
 template <class K>
 static double run(K kern, uint32_t* sink, int blocks, int threads) {
     cudaEvent_t a, b;
@@ -157,14 +334,10 @@ static double run(K kern, uint32_t* sink, int blocks, int threads) {
     return best * 1e-3;
 }
 
-int main() {
-    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
-    int sms = p.multiProcessorCount;
-    double clk = p.clockRate * 1e3;  // Hz (max)
-    uint32_t* sink; cudaMalloc(&sink, 64);
-    int threads = 256, blocks = sms * 8;
+static void sweep(uint32_t* sink, int sms, double clk, int threads, int blocks_per_sm) {
+    int blocks = sms * blocks_per_sm;
     double thr = (double)blocks * threads;
-    struct { const char* name; double ops_per_thread; double t; } R[16];
+    struct { const char* name; double ops_per_thread; double t; } R[32];
     int n = 0;
     R[n++] = {"A  IMAD.WIDE.U32 plain (64-bit acc), 8 independent", (double)ITERS * 32, run(kA, sink, blocks, threads)};
     R[n++] = {"B1 IMAD.WIDE.U32.X carry chains, 1 chain", (double)ITERS * 2 * 1 * 4, run(kB<1>, sink, blocks, threads)};
@@ -176,8 +349,28 @@ int main() {
     R[n++] = {"E  IMAD 32-bit lo, 16 independent", (double)ITERS * 32, run(kE, sink, blocks, threads)};
     R[n++] = {"F  IMAD.HI.U32, 16 independent", (double)ITERS * 32, run(kF, sink, blocks, threads)};
     R[n++] = {"G  4 carry chains + equal number of IADD (count = IMAD.WIDE)", (double)ITERS * 2 * 4 * 4, run(kG, sink, blocks, threads)};
-    printf("GPU %s, %d SMs, max clock %.0f MHz; rates in thread-instructions per clock per SM (at max clock)\n", p.name, sms, clk / 1e6);
+    R[n++] = {"H  DFMA (fma.rz.f64), 16 independent", (double)ITERS * 32, run(kH, sink, blocks, threads)};
+    R[n++] = {"I  DFMA + plain IMAD.WIDE 1:1 (count = DFMA)", (double)ITERS * 16, run(kI, sink, blocks, threads)};
+    R[n++] = {"J  plain IMAD.WIDE + IADD3 1:1 (count = IMAD.WIDE)", (double)ITERS * 16, run(kJ, sink, blocks, threads)};
+    R[n++] = {"K  plain IMAD.WIDE + SHF + LOP3 1:1:1 (count = IMAD.WIDE)", (double)ITERS * 16, run(kK, sink, blocks, threads)};
+    R[n++] = {"L  IADD3 plain, 32 independent", (double)ITERS * 32, run(kL, sink, blocks, threads)};
+    R[n++] = {"M  DFMA + 64-bit int add (add.cc/addc) 1:1 (count = DFMA)", (double)ITERS * 16, run(kM, sink, blocks, threads)};
+    R[n++] = {"N  DFMA + IMAD.WIDE + IADD3 1:1:1 (count = DFMA)", (double)ITERS * 16, run(kN, sink, blocks, threads)};
+    R[n++] = {"O  64-bit int add as add.cc/addc pairs (count = pairs)", (double)ITERS * 32, run(kO, sink, blocks, threads)};
+    R[n++] = {"P  add.u64 (count = adds)", (double)ITERS * 32, run(kP, sink, blocks, threads)};
+    R[n++] = {"Q  DADD (add.rz.f64), 16 independent", (double)ITERS * 32, run(kQ, sink, blocks, threads)};
+    printf("--- %d threads/block, %d blocks/SM = %d warps/SM\n", threads, blocks_per_sm, threads * blocks_per_sm / 32);
     for (int i = 0; i < n; i++)
         printf("%-70s %8.3f ms  %7.1f /clk/SM   %.3e /s\n", R[i].name, R[i].t * 1e3, R[i].ops_per_thread * thr / R[i].t / clk / sms, R[i].ops_per_thread * thr / R[i].t);
+}
+
+int main() {
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+    int sms = p.multiProcessorCount;
+    double clk = p.clockRate * 1e3;  // Hz (max)
+    uint32_t* sink; cudaMalloc(&sink, 64);
+    printf("GPU %s, %d SMs, max clock %.0f MHz; rates in thread-instructions per clock per SM (at max clock)\n", p.name, sms, clk / 1e6);
+    sweep(sink, sms, clk, 256, 8);
+    sweep(sink, sms, clk, 128, 4);
     return 0;
 }

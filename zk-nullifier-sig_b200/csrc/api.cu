@@ -334,8 +334,8 @@ double plume_ctx_stage_ms(plume_ctx* ctx, const char* stage, uint64_t* launches)
     return ctx->stage_ms[id];
 }
 
-int plume_measure_imad_peak(plume_ctx* ctx, int iters, double* lp_per_s) {
-    if (!ctx || !lp_per_s || iters <= 0) return PLUME_E_ARG;
+int plume_measure_imad_rates(plume_ctx* ctx, int iters, double* plain_lp_per_s, double* carry_lp_per_s) {
+    if (!ctx || iters <= 0) return PLUME_E_ARG;
     ScopedDevice sd(ctx->device);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, ctx->device));
@@ -346,21 +346,33 @@ int plume_measure_imad_peak(plume_ctx* ctx, int iters, double* lp_per_s) {
     cudaEvent_t a, b;
     CU(cudaEventCreate(&a));
     CU(cudaEventCreate(&b));
-    CU(launch_imad_peak(sink, iters, blocks, threads, s));  // warm-up
-    double best = 0;
-    for (int rep = 0; rep < 5; rep++) {
-        CU(cudaEventRecord(a, s));
-        CU(launch_imad_peak(sink, iters, blocks, threads, s));
-        CU(cudaEventRecord(b, s));
-        CU(cudaEventSynchronize(b));
-        float ms = 0;
-        CU(cudaEventElapsedTime(&ms, a, b));
-        double rate = (double)blocks * threads * (double)iters * 64.0 / (ms * 1e-3);
-        if (rate > best) best = rate;
+    double best[2] = {0, 0};
+    for (int form = 0; form < 2; form++) {
+        CU(launch_imad_peak(sink, iters, blocks, threads, form, s));  // warm-up
+        for (int rep = 0; rep < 5; rep++) {
+            CU(cudaEventRecord(a, s));
+            CU(launch_imad_peak(sink, iters, blocks, threads, form, s));
+            CU(cudaEventRecord(b, s));
+            CU(cudaEventSynchronize(b));
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, a, b));
+            double rate = (double)blocks * threads * (double)iters * 64.0 / (ms * 1e-3);
+            if (rate > best[form]) best[form] = rate;
+        }
     }
-    ctx->launches += 6;
+    ctx->launches += 12;
     cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(sink);
-    *lp_per_s = best;
+    if (plain_lp_per_s) *plain_lp_per_s = best[0];
+    if (carry_lp_per_s) *carry_lp_per_s = best[1];
+    return PLUME_OK;
+}
+
+int plume_measure_imad_peak(plume_ctx* ctx, int iters, double* lp_per_s) {
+    if (!lp_per_s) return PLUME_E_ARG;
+    double plain = 0, carry = 0;
+    int rc = plume_measure_imad_rates(ctx, iters, &plain, &carry);
+    if (rc != PLUME_OK) return rc;
+    *lp_per_s = plain > carry ? plain : carry;
     return PLUME_OK;
 }
 

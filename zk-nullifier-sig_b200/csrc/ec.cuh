@@ -35,44 +35,57 @@ PLUME_DEV bool aff_on_curve(const fe& x, const fe& y) {
     return fe_eq(lhs, rhs);
 }
 
+// Call granularity.  Default: fe_mul / fe_sqr are the out-of-line units and the point formulas are inlined
+// into their callers.  -DPLUME_POINT_FN makes jac_dbl / jac_add_aff the out-of-line units instead, with the
+// field multiplications inlined into them (no operand marshalling per multiplication, 7-11 per point call).
+#ifdef PLUME_POINT_FN
+#define EC_MUL fe_mul_inl
+#define EC_SQR fe_sqr_inl
+#define PLUME_POINTFN PLUME_DEV_NOINLINE
+#else
+#define EC_MUL fe_mul
+#define EC_SQR fe_sqr
+#define PLUME_POINTFN PLUME_DEV
+#endif
+
 // 2P, a = 0: 2M + 5S  (no point of order two exists: the group order is odd).
 // Statement order is chosen for short live ranges (the multiplier is an opaque call to the compiler,
 // so it keeps this order): at most five field elements are alive at any point.
-PLUME_DEV jac jac_dbl(const jac& p) {
+PLUME_POINTFN jac jac_dbl(jac p) {
     if (p.inf) return p;
     jac r;
-    r.z = fe_dbl(fe_mul(p.y, p.z));          // Z3 = 2*Y*Z          (Z dead)
-    fe A = fe_sqr(p.x);
-    fe B = fe_sqr(p.y);                      //                      (Y dead)
-    fe t = fe_sqr(fe_add(p.x, B));           //                      (X dead)
-    fe C = fe_sqr(B);                        //                      (B dead)
+    r.z = fe_dbl(EC_MUL(p.y, p.z));          // Z3 = 2*Y*Z          (Z dead)
+    fe A = EC_SQR(p.x);
+    fe B = EC_SQR(p.y);                      //                      (Y dead)
+    fe t = EC_SQR(fe_add(p.x, B));           //                      (X dead)
+    fe C = EC_SQR(B);                        //                      (B dead)
     fe D = fe_dbl(fe_sub(fe_sub(t, A), C));  // 2*((X+B)^2 - A - C)  (t dead)
     fe E = fe_add(fe_dbl(A), A);             // 3*A                  (A dead)
-    r.x = fe_sub(fe_sqr(E), fe_dbl(D));      // E^2 - 2*D
+    r.x = fe_sub(EC_SQR(E), fe_dbl(D));      // E^2 - 2*D
     fe C8 = fe_dbl(fe_dbl(fe_dbl(C)));
-    r.y = fe_sub(fe_mul(E, fe_sub(D, r.x)), C8);
+    r.y = fe_sub(EC_MUL(E, fe_sub(D, r.x)), C8);
     r.inf = 0;
     return r;
 }
 
 // P + Q, Q affine: 8M + 3S, ordered for short live ranges as well.
-PLUME_DEV jac jac_add_aff(const jac& p, const fe& qx, const fe& qy, uint32_t qinf) {
+PLUME_POINTFN jac jac_add_aff(jac p, fe qx, fe qy, uint32_t qinf) {
     if (qinf) return p;
     if (p.inf) { jac r; r.x = qx; r.y = qy; r.z = fe_one(); r.inf = 0; return r; }
-    fe z2 = fe_sqr(p.z);
-    fe H = fe_sub(fe_mul(qx, z2), p.x);                  // U2 - X1            (qx dead)
-    fe R = fe_sub(fe_mul(qy, fe_mul(p.z, z2)), p.y);     // S2 - Y1            (qy, z2 dead)
+    fe z2 = EC_SQR(p.z);
+    fe H = fe_sub(EC_MUL(qx, z2), p.x);                  // U2 - X1            (qx dead)
+    fe R = fe_sub(EC_MUL(qy, EC_MUL(p.z, z2)), p.y);     // S2 - Y1            (qy, z2 dead)
     if (fe_is_zero(H)) {
         if (fe_is_zero(R)) return jac_dbl(p);
         return jac_infinity();
     }
     jac r;
-    r.z = fe_mul(p.z, H);                                //                    (Z1 dead)
-    fe H2 = fe_sqr(H);
-    fe H3 = fe_mul(H, H2);                               //                    (H dead)
-    fe V = fe_mul(p.x, H2);                              //                    (X1, H2 dead)
-    r.x = fe_sub(fe_sub(fe_sqr(R), H3), fe_dbl(V));
-    r.y = fe_sub(fe_mul(R, fe_sub(V, r.x)), fe_mul(p.y, H3));
+    r.z = EC_MUL(p.z, H);                                //                    (Z1 dead)
+    fe H2 = EC_SQR(H);
+    fe H3 = EC_MUL(H, H2);                               //                    (H dead)
+    fe V = EC_MUL(p.x, H2);                              //                    (X1, H2 dead)
+    r.x = fe_sub(fe_sub(EC_SQR(R), H3), fe_dbl(V));
+    r.y = fe_sub(EC_MUL(R, fe_sub(V, r.x)), EC_MUL(p.y, H3));
     r.inf = 0;
     return r;
 }

@@ -165,11 +165,11 @@ PLUME_DEV fe fe_sub(const fe& a, const fe& b) {
 //   fe_rowNf : N lanes, the first N-1 accumulate, the last lane is entirely fresh (squaring)
 //
 // A lane can be computed two ways.  "Hard": one IMAD.WIDE.U32.X (multiply + 64-bit add + carry in/out).
-// "Soft": a plain IMAD.WIDE.U32 product followed by two IADD3.X inside the same carry chain.  The hard form
-// issues at half the rate of a plain IMAD.WIDE (profiles/r01_imad_rates.md), which suggested moving the odd
-// lanes to the ALU pipe; measured on the B200 that is 16 % SLOWER (k_sign_varbase 20.3 ms vs 17.4 ms per 2^19
-// items): the integer pipes do not overlap enough to pay for the two extra instructions.  The soft rows are
-// kept behind -DPLUME_SOFT_LANES=1 as the record of that experiment; the default is all-hard.
+// "Soft": a plain IMAD.WIDE.U32 product followed by two IADD3.X inside the same carry chain.  Both IMAD.WIDE
+// forms cost the same ~4.2 issue cycles per warp on the B200 and the additions do not overlap with them
+// (profiles/r01_imad_rates.md), so the soft form only adds instructions: measured 16 % SLOWER (k_sign_varbase
+// 20.3 ms vs 17.4 ms per 2^19 items).  The soft rows are kept behind -DPLUME_SOFT_LANES=1 as the record of that
+// experiment; the default is all-hard.
 #ifndef PLUME_SOFT_LANES
 #define PLUME_SOFT_LANES 0
 #endif

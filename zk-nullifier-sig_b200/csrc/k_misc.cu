@@ -59,27 +59,64 @@ __global__ void __launch_bounds__(128) k_debug_fe_op(int op, uint32_t n, const u
     st_fe(out + (size_t)i * 8, r);
 }
 
-// 8 independent 64-bit accumulators per thread, each fed by mad.wide.u32 (IMAD.WIDE.U32):
-// iters * 8 * 8 multiply-adds per thread, no memory traffic inside the loop.
-__global__ void k_imad_peak(uint32_t* sink, int iters) {
-    uint32_t x = threadIdx.x * 2654435761u + blockIdx.x + 1, y = x ^ 0x9E3779B9u;
-    unsigned long long a0 = x, a1 = y, a2 = x + 3, a3 = y + 5, a4 = x + 7, a5 = y + 11, a6 = x + 13, a7 = y + 17;
+// Integer-pipe microbenchmarks: the denominator of the roofline (SURVEY.md 8d "Peak").  A limb product is one
+// 32x32->64-bit multiply-accumulate.  Two forms are timed and the faster one is the peak:
+//   form 0 "columns": plain IMAD.WIDE.U32 Rd, Ra, Rb, Rc (64-bit addend, no carry flag) -- an 8x8 block of products
+//                     accumulated into 8 independent column sums per pass;
+//   form 1 "rows":    the carry-chain form the shipped multiplier uses, rows of four IMAD.WIDE.U32(.X) fused by
+//                     ptxas from mad.lo.cc / madc.hi.cc pairs, 8 independent rows per pass.
+// The multiplicands are refreshed from the accumulators on every pass (8 LOP3 per 64 products): with
+// loop-invariant operands ptxas hoists the products out of the loop and what remains is 64-bit additions
+// (that is what the round-1 version of this kernel measured; profiles/r02_issue_costs.md).
+__global__ void k_imad_peak_cols(uint32_t* sink, int iters) {
+    uint32_t a[8], b[8];
+    unsigned long long acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        a[i] = (threadIdx.x + 1) * 2654435761u + i * 40503u + blockIdx.x;
+        b[i] = a[i] ^ (0x9E3779B9u * (i + 1));
+        acc[i] = a[i];
+    }
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a0) : "r"(x), "r"(y));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a1) : "r"(y), "r"(x));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a2) : "r"(x), "r"(x));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a3) : "r"(y), "r"(y));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a4) : "r"(x), "r"(y));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a5) : "r"(y), "r"(x));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a6) : "r"(x), "r"(x));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a7) : "r"(y), "r"(y));
-        }
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[(i + j) & 7] += (unsigned long long)a[i] * b[j];
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] ^= (uint32_t)(acc[i] >> 32);
     }
-    unsigned long long t = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    unsigned long long t = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t ^= acc[i];
     if (t == 0x123456789ull) sink[0] = (uint32_t)t;  // keep the chains alive
+}
+__global__ void k_imad_peak_rows(uint32_t* sink, int iters) {
+    // loop-invariant multiplicands are fine here: ptxas keeps the fused carry-form instructions (SASS of this
+    // kernel: 16 IMAD.WIDE.U32 + 48 IMAD.WIDE.U32.X per pass, profiles/r02_issue_costs.md)
+    uint32_t x = (threadIdx.x + 1) * 2654435761u + blockIdx.x, y = x ^ 0x9E3779B9u;
+    uint32_t r[8][8];
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) r[c][k] = x + c * 8 + k;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+#pragma unroll
+            for (int c = 0; c < 8; c++)
+                asm("mad.lo.cc.u32 %0, %8, %9, %0;\n\tmadc.hi.cc.u32 %1, %8, %9, %1;\n\tmadc.lo.cc.u32 %2, %8, %9, %2;\n\tmadc.hi.cc.u32 %3, %8, %9, %3;\n\t"
+                    "madc.lo.cc.u32 %4, %8, %9, %4;\n\tmadc.hi.cc.u32 %5, %8, %9, %5;\n\tmadc.lo.cc.u32 %6, %8, %9, %6;\n\tmadc.hi.u32 %7, %8, %9, %7;"
+                    : "+r"(r[c][0]), "+r"(r[c][1]), "+r"(r[c][2]), "+r"(r[c][3]), "+r"(r[c][4]), "+r"(r[c][5]), "+r"(r[c][6]), "+r"(r[c][7])
+                    : "r"(x), "r"(y));
+    }
+    uint32_t t = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) t ^= r[c][k];
+    if (t == 0x1234567u) sink[0] = t;
 }
 
 static inline unsigned grid_for(uint32_t n, unsigned b) { return (n + b - 1) / b; }
@@ -127,8 +164,9 @@ cudaError_t launch_debug_fe_op(int op, uint32_t n, const uint32_t* a, const uint
     k_debug_fe_op<<<grid_for(n, 128), 128, 0, s>>>(op, n, a, b, out);
     return cudaGetLastError();
 }
-cudaError_t launch_imad_peak(uint32_t* sink, int iters, int blocks, int threads, cudaStream_t s) {
-    k_imad_peak<<<blocks, threads, 0, s>>>(sink, iters);
+cudaError_t launch_imad_peak(uint32_t* sink, int iters, int blocks, int threads, int form, cudaStream_t s) {
+    if (form == 0) k_imad_peak_cols<<<blocks, threads, 0, s>>>(sink, iters);
+    else k_imad_peak_rows<<<blocks, threads, 0, s>>>(sink, iters);
     return cudaGetLastError();
 }
 

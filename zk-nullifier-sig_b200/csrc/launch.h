@@ -55,7 +55,7 @@ cudaError_t launch_gtab_bases(uint32_t* bases, int w, cudaStream_t s);
 cudaError_t launch_gtab_entries(uint32_t ne, uint32_t* tab, uint32_t* zs, const uint32_t* bases, int w, cudaStream_t s);
 cudaError_t launch_gtab_norm(uint32_t ne, uint32_t* tab, const uint32_t* zs, cudaStream_t s);
 // integer-pipe microbenchmark: every thread runs `iters` * 64 independent-chain IMAD.WIDE.U32
-cudaError_t launch_imad_peak(uint32_t* sink, int iters, int blocks, int threads, cudaStream_t s);
+cudaError_t launch_imad_peak(uint32_t* sink, int iters, int blocks, int threads, int form, cudaStream_t s);  // 64 limb products per thread per iteration
 cudaError_t launch_sec1_compress(uint32_t n, const uint8_t* in64, uint8_t* out33, cudaStream_t s);
 cudaError_t launch_sec1_decompress(uint32_t n, const uint8_t* in33, uint8_t* out64, uint8_t* ok, cudaStream_t s);
 cudaError_t launch_and_flags(uint32_t n, uint8_t* ok, const uint8_t* f0, const uint8_t* f1, const uint8_t* f2, const uint8_t* f3, cudaStream_t s);

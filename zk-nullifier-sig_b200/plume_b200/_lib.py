@@ -39,6 +39,7 @@ SYMBOLS = {
     "plume_ctx_stage_ms": (ctypes.c_double, [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint64)]),
     "plume_debug_fe_op": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, _u8p, _u8p, _u8p]),
     "plume_measure_imad_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
+    "plume_measure_imad_rates": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
 }
 
 

@@ -107,6 +107,12 @@ class PlumeContext:
         self._check(self._lib.plume_measure_imad_peak(self._h, iters, ctypes.byref(v)), "plume_measure_imad_peak")
         return v.value
 
+    def measure_imad_rates(self, iters=4096):
+        """(plain IMAD.WIDE.U32, carry-chain IMAD.WIDE.U32.X) limb products per second."""
+        p, c = ctypes.c_double(0), ctypes.c_double(0)
+        self._check(self._lib.plume_measure_imad_rates(self._h, iters, ctypes.byref(p), ctypes.byref(c)), "plume_measure_imad_rates")
+        return p.value, c.value
+
     def debug_fe_op(self, op, a, b):
         """plume_debug_fe_op on u32[n,8] little-endian limb arrays."""
         a = np.ascontiguousarray(a, dtype=np.uint32); b = np.ascontiguousarray(b, dtype=np.uint32)
