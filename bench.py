@@ -43,9 +43,11 @@ ORDER = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
 LP_PER_M = 72
 WORK_M = {"sign": 4500, "verify": 4900, "h2c": 910,
           "sign_varbase": 2830,            # pair of scalar multiplications sharing the base h
-          "verify_muls": 1770 + 2200}      # G*s - pk*c and h*s - nul*c
+          "verify_muls": 1770 + 2200,      # G*s - pk*c and h*s - nul*c as one kernel (-DPLUME_VERIFY_FUSED builds)
+          "verify_mul_a": 1770, "verify_mul_b": 2200}
 # algorithmic bytes per item of the dominant kernels (what they must read + write in HBM)
-BYTES = {"sign_varbase": 3 * 32 + 64 + 2 * 32 + 6 * 32, "verify_muls": 3 * 32 + 64 * 2 + 64 + 2 * 32 + 6 * 32}
+BYTES = {"sign_varbase": 3 * 32 + 64 + 2 * 32 + 6 * 32, "verify_muls": 3 * 32 + 64 * 2 + 64 + 2 * 32 + 6 * 32,
+         "verify_mul_a": 64 + 2 * 32 + 3 * 32, "verify_mul_b": 3 * 32 + 64 + 2 * 32 + 2 * 32 + 3 * 32}
 
 
 def synth_inputs(seed, first, count):
@@ -327,7 +329,7 @@ def main():
     dev_ms = e0.elapsed_time(e1)
     launches = ctx.launch_count - launches0
     stage = {}
-    for st in ("sign_fixed", "sign_h2c", "sign_varbase", "sign_final", "verify_h2c", "verify_muls", "verify_final", "h2c_map",
+    for st in ("sign_fixed", "sign_h2c", "sign_varbase", "sign_final", "verify_h2c", "verify_muls", "verify_mul_a", "verify_mul_b", "verify_final", "h2c_map",
                "h2c_out", "binv", "sec1_compress", "sec1_decompress"):
         ms, k = ctx.stage_ms(st)
         if k:

@@ -26,7 +26,7 @@ for ver in (1, 2):
     t = time.time(); ok = ctx.verify_batch(ver, msgs, o["pk"], o["nullifier"], o["c"], o["s"], o["r_point"], o["hashed_to_curve_r"]); dt = time.time() - t
     print("verify v%d: %.1f ms wall -> %.3e /s; ok=%d" % (ver, dt * 1e3, n / dt, int(ok.sum())))
     tot = 0
-    for st in ("verify_h2c", "verify_muls", "verify_final", "binv"):
+    for st in ("verify_h2c", "verify_mul_b", "verify_mul_a", "verify_final", "binv"):
         ms, k = ctx.stage_ms(st); tot += ms
         print("   %-13s %8.3f ms  (%d launches)" % (st, ms, k))
     print("   kernels total %.3f ms -> %.3e ver/s" % (tot, n / (tot * 1e-3)))

@@ -11,6 +11,19 @@ __global__ void __launch_bounds__(PLUME_VM_BLOCK, PLUME_VM_MINBLOCKS) k_verify_m
         verify_stage_muls(i, a, vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS},
                           vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS + VB_TAB_WORDS});
 }
+#ifndef PLUME_VA_MINBLOCKS
+#define PLUME_VA_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(PLUME_VM_BLOCK, PLUME_VM_MINBLOCKS) k_verify_mul_b(verify_args a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n)
+        verify_stage_mul_b(i, a, vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS},
+                           vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS + VB_TAB_WORDS});
+}
+__global__ void __launch_bounds__(PLUME_VM_BLOCK, PLUME_VA_MINBLOCKS) k_verify_mul_a(verify_args a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) verify_stage_mul_a(i, a, vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS});
+}
 __global__ void __launch_bounds__(128) k_verify_final(verify_args a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.n) verify_stage_final(i, a);
@@ -22,8 +35,16 @@ cudaError_t launch_verify_h2c(const verify_args& a, cudaStream_t s) {
     k_verify_h2c<<<grid_for(a.n, 128), 128, 0, s>>>(a);
     return cudaGetLastError();
 }
-cudaError_t launch_verify_muls(const verify_args& a, cudaStream_t s) {
+cudaError_t launch_verify_muls(const verify_args& a, cudaStream_t s) {   // fused form (-DPLUME_VERIFY_FUSED)
     k_verify_muls<<<grid_for(a.n, PLUME_VM_BLOCK), PLUME_VM_BLOCK, 0, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_verify_mul_b(const verify_args& a, cudaStream_t s) {
+    k_verify_mul_b<<<grid_for(a.n, PLUME_VM_BLOCK), PLUME_VM_BLOCK, 0, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_verify_mul_a(const verify_args& a, cudaStream_t s) {
+    k_verify_mul_a<<<grid_for(a.n, PLUME_VM_BLOCK), PLUME_VM_BLOCK, 0, s>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_verify_final(const verify_args& a, cudaStream_t s) {

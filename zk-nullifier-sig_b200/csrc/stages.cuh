@@ -432,6 +432,51 @@ PLUME_DEV void verify_stage_muls(uint32_t i, const verify_args& a, const Tab& ta
     ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, B);
 }
 
+// The same work as two kernels (launched B first: it consumes the inverted Z of h in WS_Z0, which A's result then
+// overwrites).  Each half has its own register budget.
+template <class Tab>
+PLUME_DEV void verify_stage_mul_b(uint32_t i, const verify_args& a, const Tab& tab1, const Tab& tab2) {
+    aff h = ws_load_affine(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i);
+    ws_store_aff(a.ws, a.n, WS_HX, WS_HY, i, h);
+    st_fe(ws_at(a.ws, a.n, WS_RX, i), fe_set_u32(h.inf));
+    aff nul;
+    bool good = a.ok[i] != 0;
+    sc c = sc_one(), s = sc_one();
+    if (good) {
+        ld_point_be(nul, a.nullifier + (size_t)i * 64);
+        c = ld_sc_be(a.c + (size_t)i * 32);
+        s = ld_sc_be(a.s + (size_t)i * 32);
+    } else {
+        nul = aff_generator();
+    }
+    sc mc = sc_neg(c);
+    jac B;
+    if (!h.inf && !nul.inf) {
+        fe zg = vb_build_table_pair(h.x, h.y, tab1, nul.x, nul.y, tab2);
+        B = vb_mul2_tab(s, tab1, mc, tab2, zg);
+    } else {
+        B = jac_add(vb_mul_point(h, s, tab1), vb_mul_point(nul, mc, tab1));
+    }
+    ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, B);
+}
+template <class Tab>
+PLUME_DEV void verify_stage_mul_a(uint32_t i, const verify_args& a, const Tab& tab1) {
+    aff pk;
+    bool good = a.ok[i] != 0;
+    sc c = sc_one(), s = sc_one();
+    if (good) {
+        ld_point_be(pk, a.pk + (size_t)i * 64);
+        c = ld_sc_be(a.c + (size_t)i * 32);
+        s = ld_sc_be(a.s + (size_t)i * 32);
+    } else {
+        pk = aff_generator();
+    }
+    sc mc = sc_neg(c);
+    jac A = fb_mul(s, a.gtab, a.gw);
+    A = jac_add(A, vb_mul_point(pk, mc, tab1));
+    ws_store_jac(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i, A);
+}
+
 PLUME_DEV void verify_stage_final(uint32_t i, const verify_args& a) {
     bool good = a.ok[i] != 0;
     if (!good) { a.ok[i] = 0; return; }
