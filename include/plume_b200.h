@@ -50,6 +50,7 @@ extern "C" {
 #define PLUME_STATUS_BAD_C 3    /* SHA-256 output c = 0 or c >= n (NonZeroScalar::from_repr, :90-91) */
 #define PLUME_STATUS_ZERO_S 4   /* s = r + c*sk = 0 (:95) */
 #define PLUME_STATUS_H_INF 5    /* hash_to_curve returned the identity (:61) */
+#define PLUME_STATUS_BAD_PK 6   /* arkworks flavour: pk is the identity (hash_to_curve fails, rust-arkworks/src/lib.rs:97-100) or not a curve point */
 
 typedef struct plume_ctx plume_ctx;
 
@@ -135,6 +136,39 @@ int plume_verify_batch_sec1(plume_ctx* ctx, int version, size_t n,
                             const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
                             const uint8_t* pk33, const uint8_t* nullifier33, const uint8_t* c, const uint8_t* s,
                             const uint8_t* r_point33, const uint8_t* hashed_to_curve_r33, uint8_t* ok);
+
+/*
+ * arkworks flavour: the same path with the semantics of the twin crate `plume_arkworks`.
+ *   plume_ark_sign_batch    replaces sign_with_r (rust-arkworks/src/lib.rs:229-278; `sign`, :281-291, is the same after
+ *                           r = Fr::rand(rng) on the caller's side).  The public key is an INPUT (the keypair's first half,
+ *                           it is not recomputed from sk); r and sk are any Fr, zero included (r = 0 gives identity
+ *                           r_point / hashed_to_curve_r, encoded as the single byte 00 in the challenge, :112-118);
+ *                           digest_private = SHA-256(...) reduced mod n (:257); s = r + sk * c; nothing is rejected but
+ *                           scalars >= n (PLUME_STATUS_BAD_R / BAD_SK) and pk = identity or off-curve (PLUME_STATUS_BAD_PK).
+ *                           Outputs map onto PlumeSignaturePublic {s, nullifier} and PlumeSignaturePrivate
+ *                           {hashed_to_curve_r, r_point, digest_private} (:175-201).
+ *   plume_ark_verify_batch  replaces verify_non_zk (rust-arkworks/src/tests.rs:28-78): r_point and hashed_to_curve_r are
+ *                           required and compared in BOTH versions; ok[i] = 1 iff it returns Ok(true); an identity pk
+ *                           (Err in the reference) gives 0.
+ */
+int plume_ark_sign_batch(plume_ctx* ctx, int version, size_t n,
+                         const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                         const uint8_t* pk, const uint8_t* sk, const uint8_t* r,
+                         uint8_t* nullifier, uint8_t* digest_private, uint8_t* s,
+                         uint8_t* r_point, uint8_t* hashed_to_curve_r, uint8_t* status);
+int plume_ark_verify_batch(plume_ctx* ctx, int version, size_t n,
+                           const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                           const uint8_t* pk, const uint8_t* nullifier, const uint8_t* digest_private, const uint8_t* s,
+                           const uint8_t* r_point, const uint8_t* hashed_to_curve_r, uint8_t* ok);
+int plume_ark_sign_batch_device(plume_ctx* ctx, int version, size_t n,
+                                const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                                const uint8_t* pk, const uint8_t* sk, const uint8_t* r,
+                                uint8_t* nullifier, uint8_t* digest_private, uint8_t* s,
+                                uint8_t* r_point, uint8_t* hashed_to_curve_r, uint8_t* status, void* stream);
+int plume_ark_verify_batch_device(plume_ctx* ctx, int version, size_t n,
+                                  const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                                  const uint8_t* pk, const uint8_t* nullifier, const uint8_t* digest_private, const uint8_t* s,
+                                  const uint8_t* r_point, const uint8_t* hashed_to_curve_r, uint8_t* ok, void* stream);
 
 /* Device-pointer variants: all pointers are device memory of the context's GPU, `stream` is a
  * cudaStream_t (passed as void* to keep CUDA headers out of this file).  n must not exceed

@@ -253,6 +253,53 @@ def verify(version, msg, pk, nul, c, s, r_point=None, hashed_to_curve_r=None):
     return c == int.from_bytes(d, "big") % N                    # Scalar::reduce
 
 
+# ---- the arkworks twin (rust-arkworks/src/lib.rs) ------------------------------------------------------
+ST_BAD_PK = 6
+
+
+def ark_sign_with_r(version, msg, pk, sk, r):
+    """rust-arkworks/src/lib.rs:229-278.  pk: affine tuple (INF makes hash_to_curve fail, :97-100); sk, r: Fr, i.e.
+    ints in [0, n).  Returns (status, dict): nothing else is rejected, c is reduced mod n (:257)."""
+    if not (0 <= r < N):
+        return ST_BAD_R, None
+    if not (0 <= sk < N):
+        return ST_BAD_SK, None
+    if pk is INF:
+        return ST_BAD_PK, None
+    r_point = pt_mul(G, r) if r else INF                         # :235
+    h = hash_to_curve(msg, pk)                                   # :238
+    z = pt_mul(h, r) if r else INF                               # :241
+    nul = pt_mul(h, sk) if sk else INF                           # :244
+    if version == 1:                                             # :247-256 (identity -> the byte 00, :112-118)
+        c = c_sha256_vec_signal([G, pk, h, nul, r_point, z])
+    else:
+        c = c_sha256_vec_signal([nul, r_point, z])
+    ci = int.from_bytes(c, "big") % N                            # :257
+    s = (r + sk * ci) % N                                        # :259-260
+    return ST_OK, dict(nullifier=nul, digest_private=ci, s=s, r_point=r_point, hashed_to_curve_r=z, h=h)
+
+
+def ark_verify_non_zk(version, msg, pk, nul, digest_private, s, r_point, hashed_to_curve_r):
+    """rust-arkworks/src/tests.rs:28-78: Ok(bool); an identity pk is Err (returned as None here)."""
+    if pk is INF:
+        return None
+    h = hash_to_curve(msg, pk)                                                       # :36
+    if version == 1:                                                                 # :40-52
+        c = c_sha256_vec_signal([G, pk, h, nul, r_point, hashed_to_curve_r])
+    else:
+        c = c_sha256_vec_signal([nul, r_point, hashed_to_curve_r])
+    ci = int.from_bytes(c, "big") % N                                                # :53
+    gs = pt_mul(G, s) if s else INF
+    pkc = pt_mul(pk, digest_private) if digest_private else INF
+    if r_point != pt_add(gs, pt_neg(pkc)):                                           # :56-62
+        return False
+    hs = pt_mul(h, s) if s and h is not INF else INF
+    nc = pt_mul(nul, digest_private) if digest_private and nul is not INF else INF
+    if hashed_to_curve_r != pt_add(hs, pt_neg(nc)):                                  # :65-71
+        return False
+    return ci == digest_private                                                      # :74
+
+
 def compress33(p):
     """33-byte SEC1 slot: 02/03 || x, identity = 00 followed by zeros."""
     return bytes(33) if p is INF else encode_pt(p)

@@ -55,6 +55,29 @@ def _msgs(msgs):
     return np.ascontiguousarray(blob), offs
 
 
+def ark_sign_batch(version, msgs, pk, sk, r, gw=8, binv_threads=3):
+    """arkworks flavour: pk is an input; returns nullifier, digest_private, s, r_point, hashed_to_curve_r, status."""
+    n = len(msgs)
+    blob, offs = _msgs(msgs)
+    pk = np.frombuffer(pk, dtype=np.uint8).copy(); sk = np.frombuffer(sk, dtype=np.uint8).copy(); r = np.frombuffer(r, dtype=np.uint8).copy()
+    o = {k: np.zeros((n, w), dtype=np.uint8) for k, w in
+         (("nullifier", 64), ("digest_private", 32), ("s", 32), ("r_point", 64), ("hashed_to_curve_r", 64))}
+    o["status"] = np.zeros(n, dtype=np.uint8)
+    lib().hs_sign_batch(1, version, n, _p(blob), _p(offs), 0, _p(sk), _p(r), _p(pk), _p(o["nullifier"]), _p(o["digest_private"]),
+                        _p(o["s"]), _p(o["r_point"]), _p(o["hashed_to_curve_r"]), _p(o["status"]), gw, binv_threads)
+    return o
+
+
+def ark_verify_batch(version, msgs, pk, nullifier, digest_private, s, r_point, hashed_to_curve_r, gw=8, binv_threads=3):
+    n = len(msgs)
+    blob, offs = _msgs(msgs)
+    a = [np.ascontiguousarray(x, dtype=np.uint8) for x in (pk, nullifier, digest_private, s, r_point, hashed_to_curve_r)]
+    ok = np.zeros(n, dtype=np.uint8)
+    lib().hs_verify_batch(1, version, n, _p(blob), _p(offs), 0, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), _p(a[5]), _p(ok),
+                          gw, binv_threads, 0)
+    return ok
+
+
 def sign_batch(version, msgs, sk, r, gw=8, binv_threads=3):
     n = len(msgs)
     blob, offs = _msgs(msgs)
@@ -62,18 +85,18 @@ def sign_batch(version, msgs, sk, r, gw=8, binv_threads=3):
     o = {k: np.zeros((n, w), dtype=np.uint8) for k, w in
          (("pk", 64), ("nullifier", 64), ("c", 32), ("s", 32), ("r_point", 64), ("hashed_to_curve_r", 64))}
     o["status"] = np.zeros(n, dtype=np.uint8)
-    lib().hs_sign_batch(version, n, _p(blob), _p(offs), 0, _p(sk), _p(r), _p(o["pk"]), _p(o["nullifier"]), _p(o["c"]), _p(o["s"]),
+    lib().hs_sign_batch(0, version, n, _p(blob), _p(offs), 0, _p(sk), _p(r), _p(o["pk"]), _p(o["nullifier"]), _p(o["c"]), _p(o["s"]),
                         _p(o["r_point"]), _p(o["hashed_to_curve_r"]), _p(o["status"]), gw, binv_threads)
     return o
 
 
-def verify_batch(version, msgs, pk, nullifier, c, s, r_point, hashed_to_curve_r, gw=8, binv_threads=3):
+def verify_batch(version, msgs, pk, nullifier, c, s, r_point, hashed_to_curve_r, gw=8, binv_threads=3, fused=False):
     n = len(msgs)
     blob, offs = _msgs(msgs)
     a = [np.ascontiguousarray(x, dtype=np.uint8) for x in (pk, nullifier, c, s, r_point, hashed_to_curve_r)]
     ok = np.zeros(n, dtype=np.uint8)
-    lib().hs_verify_batch(version, n, _p(blob), _p(offs), 0, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), _p(a[5]), _p(ok),
-                          gw, binv_threads)
+    lib().hs_verify_batch(0, version, n, _p(blob), _p(offs), 0, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), _p(a[5]), _p(ok),
+                          gw, binv_threads, 1 if fused else 0)
     return ok
 
 

@@ -107,14 +107,16 @@ void hs_fb_mul(const uint8_t* k32, int w, uint8_t* out64) {
     st_point_be(out64, q);
 }
 
-int hs_sign_batch(int version, uint32_t n, const uint8_t* msgs, const uint64_t* offs, uint32_t msg_len,
+// flavour 0: k256 (pk is an output), 1: arkworks (pk is an input)
+int hs_sign_batch(int flavour, int version, uint32_t n, const uint8_t* msgs, const uint64_t* offs, uint32_t msg_len,
                   const uint8_t* sk, const uint8_t* r, uint8_t* pk, uint8_t* nul, uint8_t* c, uint8_t* s,
                   uint8_t* r_point, uint8_t* hr, uint8_t* status, int gw, uint32_t binv_threads) {
     build_gtab(gw);
     std::vector<uint32_t> ws((size_t)WS_SLOTS * n * 8);
-    sign_args a;
-    a.version = version; a.n = n; a.msgs.base = msgs; a.msgs.offs = offs; a.msgs.fixed_len = msg_len;
-    a.sk = sk; a.r = r; a.pk = pk; a.nullifier = nul; a.c = c; a.s = s; a.r_point = r_point; a.hashed_to_curve_r = hr;
+    sign_args a{};
+    a.version = version; a.flavour = flavour; a.n = n; a.msgs.base = msgs; a.msgs.offs = offs; a.msgs.fixed_len = msg_len;
+    a.sk = sk; a.r = r; a.pk = flavour ? nullptr : pk; a.pk_in = flavour ? pk : nullptr;
+    a.nullifier = nul; a.c = c; a.s = s; a.r_point = r_point; a.hashed_to_curve_r = hr;
     a.status = status; a.ws = ws.data(); a.gtab = g_tab.data(); a.gw = gw; a.vbtab = nullptr;
     uint32_t tabw[VB_TAB_WORDS * 4];
     for (uint32_t i = 0; i < n; i++) sign_stage_fixed(i, a);
@@ -131,19 +133,25 @@ int hs_sign_batch(int version, uint32_t n, const uint8_t* msgs, const uint64_t* 
     return 0;
 }
 
-int hs_verify_batch(int version, uint32_t n, const uint8_t* msgs, const uint64_t* offs, uint32_t msg_len,
+// fused != 0 runs the one-kernel form of the multiplication stage (-DPLUME_VERIFY_FUSED builds), else the shipped two
+int hs_verify_batch(int flavour, int version, uint32_t n, const uint8_t* msgs, const uint64_t* offs, uint32_t msg_len,
                     const uint8_t* pk, const uint8_t* nul, const uint8_t* c, const uint8_t* s,
-                    const uint8_t* r_point, const uint8_t* hr, uint8_t* ok, int gw, uint32_t binv_threads) {
+                    const uint8_t* r_point, const uint8_t* hr, uint8_t* ok, int gw, uint32_t binv_threads, int fused) {
     build_gtab(gw);
     std::vector<uint32_t> ws((size_t)WS_SLOTS * n * 8);
-    verify_args a;
-    a.version = version; a.n = n; a.msgs.base = msgs; a.msgs.offs = offs; a.msgs.fixed_len = msg_len;
+    verify_args a{};
+    a.version = version; a.flavour = flavour; a.n = n; a.msgs.base = msgs; a.msgs.offs = offs; a.msgs.fixed_len = msg_len;
     a.pk = pk; a.nullifier = nul; a.c = c; a.s = s; a.r_point = r_point; a.hashed_to_curve_r = hr;
     a.ok = ok; a.ws = ws.data(); a.gtab = g_tab.data(); a.gw = gw; a.vbtab = nullptr;
     uint32_t tabw[VB_TAB_WORDS * 4];
     for (uint32_t i = 0; i < n; i++) verify_stage_h2c(i, a);
     run_binv(a.ws, n, n, binv_threads);
-    for (uint32_t i = 0; i < n; i++) verify_stage_muls(i, a, vb_tab_linear{tabw}, vb_tab_linear{tabw + VB_TAB_WORDS});
+    if (fused) {
+        for (uint32_t i = 0; i < n; i++) verify_stage_muls(i, a, vb_tab_linear{tabw}, vb_tab_linear{tabw + VB_TAB_WORDS});
+    } else {
+        for (uint32_t i = 0; i < n; i++) verify_stage_mul_b(i, a, vb_tab_linear{tabw}, vb_tab_linear{tabw + VB_TAB_WORDS});
+        for (uint32_t i = 0; i < n; i++) verify_stage_mul_a(i, a, vb_tab_linear{tabw});
+    }
     run_binv(a.ws, n, 2 * n, binv_threads);
     for (uint32_t i = 0; i < n; i++) verify_stage_final(i, a);
     return 0;

@@ -404,42 +404,75 @@ int plume_debug_fe_op(plume_ctx* ctx, int op, size_t n, const uint32_t* a, const
 }
 
 // ---- device-pointer variants ---------------------------------------------------------------------------------
-int plume_sign_batch_device(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets,
-                            size_t msg_len, const uint8_t* sk, const uint8_t* r, uint8_t* pk, uint8_t* nullifier,
-                            uint8_t* c, uint8_t* s_out, uint8_t* r_point, uint8_t* hashed_to_curve_r, uint8_t* status,
-                            void* stream) {
+}  // extern "C" (reopened below)
+
+namespace {
+int sign_device(plume_ctx* ctx, int flavour, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                const uint8_t* pk_in, const uint8_t* sk, const uint8_t* r, uint8_t* pk, uint8_t* nullifier, uint8_t* c, uint8_t* s_out,
+                uint8_t* r_point, uint8_t* hashed_to_curve_r, uint8_t* status, void* stream) {
     if (!ctx) return PLUME_E_ARG;
     if (version != 1 && version != 2) return fail(ctx, PLUME_E_ARG, "version must be 1 or 2");
     if (n == 0) return PLUME_OK;
     if (n > ctx->chunk) return fail(ctx, PLUME_E_ARG, "n exceeds plume_ctx_chunk_items()");
-    if (!sk || !r || !pk || !nullifier || !c || !s_out || !status) return fail(ctx, PLUME_E_ARG, "null array");
+    if (!sk || !r || !nullifier || !c || !s_out || !status) return fail(ctx, PLUME_E_ARG, "null array");
+    if (flavour == PLUME_FLAVOUR_ARKWORKS ? !pk_in : !pk) return fail(ctx, PLUME_E_ARG, "null pk array");
     ScopedDevice sd(ctx->device);
-    sign_args a;
-    a.version = version; a.n = (uint32_t)n;
+    sign_args a{};
+    a.version = version; a.flavour = flavour; a.n = (uint32_t)n;
     a.msgs.base = msgs; a.msgs.offs = msg_offsets; a.msgs.fixed_len = (uint32_t)msg_len;
-    a.sk = sk; a.r = r; a.pk = pk; a.nullifier = nullifier; a.c = c; a.s = s_out;
-    a.r_point = r_point; a.hashed_to_curve_r = hashed_to_curve_r; a.status = status;
+    a.sk = sk; a.r = r; a.pk = pk; a.pk_in = pk_in; a.nullifier = nullifier; a.c = c; a.s = s_out; a.r_point = r_point;
+    a.hashed_to_curve_r = hashed_to_curve_r; a.status = status;
     a.ws = ctx->lanes[0].ws; a.gtab = ctx->gtab; a.gw = ctx->gw; a.vbtab = ctx->lanes[0].vbtab;
     return enqueue_sign(ctx, a, (cudaStream_t)stream);
 }
-
-int plume_verify_batch_device(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets,
-                              size_t msg_len, const uint8_t* pk, const uint8_t* nullifier, const uint8_t* c,
-                              const uint8_t* s_in, const uint8_t* r_point, const uint8_t* hashed_to_curve_r, uint8_t* ok,
-                              void* stream) {
+int verify_device(plume_ctx* ctx, int flavour, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                  const uint8_t* pk, const uint8_t* nullifier, const uint8_t* c, const uint8_t* s_in, const uint8_t* r_point,
+                  const uint8_t* hashed_to_curve_r, uint8_t* ok, void* stream) {
     if (!ctx) return PLUME_E_ARG;
     if (version != 1 && version != 2) return fail(ctx, PLUME_E_ARG, "version must be 1 or 2");
     if (n == 0) return PLUME_OK;
     if (n > ctx->chunk) return fail(ctx, PLUME_E_ARG, "n exceeds plume_ctx_chunk_items()");
     if (!pk || !nullifier || !c || !s_in || !ok) return fail(ctx, PLUME_E_ARG, "null array");
-    if (version == 1 && (!r_point || !hashed_to_curve_r)) return fail(ctx, PLUME_E_ARG, "V1 needs r_point and hashed_to_curve_r");
+    if ((version == 1 || flavour == PLUME_FLAVOUR_ARKWORKS) && (!r_point || !hashed_to_curve_r))
+        return fail(ctx, PLUME_E_ARG, "r_point and hashed_to_curve_r are required");
     ScopedDevice sd(ctx->device);
-    verify_args a;
-    a.version = version; a.n = (uint32_t)n;
+    verify_args a{};
+    a.version = version; a.flavour = flavour; a.n = (uint32_t)n;
     a.msgs.base = msgs; a.msgs.offs = msg_offsets; a.msgs.fixed_len = (uint32_t)msg_len;
     a.pk = pk; a.nullifier = nullifier; a.c = c; a.s = s_in; a.r_point = r_point; a.hashed_to_curve_r = hashed_to_curve_r;
     a.ok = ok; a.ws = ctx->lanes[0].ws; a.gtab = ctx->gtab; a.gw = ctx->gw; a.vbtab = ctx->lanes[0].vbtab;
     return enqueue_verify(ctx, a, (cudaStream_t)stream);
+}
+}  // namespace
+
+extern "C" {
+
+int plume_sign_batch_device(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets,
+                            size_t msg_len, const uint8_t* sk, const uint8_t* r, uint8_t* pk, uint8_t* nullifier, uint8_t* c,
+                            uint8_t* s_out, uint8_t* r_point, uint8_t* hashed_to_curve_r, uint8_t* status, void* stream) {
+    return sign_device(ctx, PLUME_FLAVOUR_K256, version, n, msgs, msg_offsets, msg_len, nullptr, sk, r, pk, nullifier, c, s_out, r_point,
+                       hashed_to_curve_r, status, stream);
+}
+int plume_ark_sign_batch_device(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets,
+                                size_t msg_len, const uint8_t* pk, const uint8_t* sk, const uint8_t* r, uint8_t* nullifier,
+                                uint8_t* digest_private, uint8_t* s_out, uint8_t* r_point, uint8_t* hashed_to_curve_r, uint8_t* status,
+                                void* stream) {
+    return sign_device(ctx, PLUME_FLAVOUR_ARKWORKS, version, n, msgs, msg_offsets, msg_len, pk, sk, r, nullptr, nullifier,
+                       digest_private, s_out, r_point, hashed_to_curve_r, status, stream);
+}
+int plume_verify_batch_device(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets,
+                              size_t msg_len, const uint8_t* pk, const uint8_t* nullifier, const uint8_t* c,
+                              const uint8_t* s_in, const uint8_t* r_point, const uint8_t* hashed_to_curve_r, uint8_t* ok,
+                              void* stream) {
+    return verify_device(ctx, PLUME_FLAVOUR_K256, version, n, msgs, msg_offsets, msg_len, pk, nullifier, c, s_in, r_point,
+                         hashed_to_curve_r, ok, stream);
+}
+int plume_ark_verify_batch_device(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets,
+                                  size_t msg_len, const uint8_t* pk, const uint8_t* nullifier, const uint8_t* digest_private,
+                                  const uint8_t* s_in, const uint8_t* r_point, const uint8_t* hashed_to_curve_r, uint8_t* ok,
+                                  void* stream) {
+    return verify_device(ctx, PLUME_FLAVOUR_ARKWORKS, version, n, msgs, msg_offsets, msg_len, pk, nullifier, digest_private, s_in,
+                         r_point, hashed_to_curve_r, ok, stream);
 }
 
 int plume_hash_to_curve_batch_device(plume_ctx* ctx, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets,
@@ -457,13 +490,17 @@ int plume_hash_to_curve_batch_device(plume_ctx* ctx, size_t n, const uint8_t* ms
 }
 
 // ---- host-pointer variants: chunked, two lanes in flight --------------------------------------------------------
-int plume_sign_batch(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets,
-                     size_t msg_len, const uint8_t* sk, const uint8_t* r, uint8_t* pk, uint8_t* nullifier, uint8_t* c,
-                     uint8_t* s_out, uint8_t* r_point, uint8_t* hashed_to_curve_r, uint8_t* status) {
+}  // extern "C" (reopened below)
+
+namespace {
+int sign_host(plume_ctx* ctx, int flavour, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+              const uint8_t* pk_in, const uint8_t* sk, const uint8_t* r, uint8_t* pk, uint8_t* nullifier, uint8_t* c, uint8_t* s_out,
+              uint8_t* r_point, uint8_t* hashed_to_curve_r, uint8_t* status) {
     if (int rc = check_common(ctx, n, msgs, msg_offsets, msg_len)) return rc;
     if (version != 1 && version != 2) return fail(ctx, PLUME_E_ARG, "version must be 1 or 2");
     if (n == 0) return PLUME_OK;
-    if (!sk || !r || !pk || !nullifier || !c || !s_out || !status) return fail(ctx, PLUME_E_ARG, "null array");
+    if (!sk || !r || !nullifier || !c || !s_out || !status) return fail(ctx, PLUME_E_ARG, "null array");
+    if (flavour == PLUME_FLAVOUR_ARKWORKS ? !pk_in : !pk) return fail(ctx, PLUME_E_ARG, "null pk array");
     ScopedDevice sd(ctx->device);
     size_t k = 0;
     for (size_t i0 = 0; i0 < n; i0 += ctx->chunk, k++) {
@@ -473,15 +510,16 @@ int plume_sign_batch(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs,
         if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * (64 + 64 * 4 + 64 + 1) + 4096)) return rc;
         L.d_io_used = 0;
         L.busy = true;
-        sign_args a;
-        a.version = version; a.n = (uint32_t)cn;
+        sign_args a{};
+        a.version = version; a.flavour = flavour; a.n = (uint32_t)cn;
         if (int rc = lane_msgs(ctx, L, msgs, msg_offsets, msg_len, i0, cn, &a.msgs)) return rc;
-        uint8_t *d_sk, *d_r;
+        uint8_t *d_sk, *d_r, *d_pk = nullptr;
         if (int rc = lane_input(ctx, L, sk + i0 * 32, cn * 32, &d_sk)) return rc;
         if (int rc = lane_input(ctx, L, r + i0 * 32, cn * 32, &d_r)) return rc;
-        a.sk = d_sk; a.r = d_r;
-        size_t o_pk, o_nul, o_c, o_s, o_rp = 0, o_hr = 0, o_st;
-        a.pk = lane_output(L, cn * 64, &o_pk);
+        if (pk_in) if (int rc = lane_input(ctx, L, pk_in + i0 * 64, cn * 64, &d_pk)) return rc;
+        a.sk = d_sk; a.r = d_r; a.pk_in = d_pk;
+        size_t o_pk = 0, o_nul, o_c, o_s, o_rp = 0, o_hr = 0, o_st;
+        a.pk = pk ? lane_output(L, cn * 64, &o_pk) : nullptr;
         a.nullifier = lane_output(L, cn * 64, &o_nul);
         a.c = lane_output(L, cn * 32, &o_c);
         a.s = lane_output(L, cn * 32, &o_s);
@@ -490,7 +528,7 @@ int plume_sign_batch(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs,
         a.status = lane_output(L, cn, &o_st);
         a.ws = L.ws; a.gtab = ctx->gtab; a.gw = ctx->gw; a.vbtab = L.vbtab;
         if (int rc = enqueue_sign(ctx, a, L.stream)) return rc;
-        if (int rc = lane_fetch(ctx, L, pk + i0 * 64, o_pk, cn * 64)) return rc;
+        if (pk) if (int rc = lane_fetch(ctx, L, pk + i0 * 64, o_pk, cn * 64)) return rc;
         if (int rc = lane_fetch(ctx, L, nullifier + i0 * 64, o_nul, cn * 64)) return rc;
         if (int rc = lane_fetch(ctx, L, c + i0 * 32, o_c, cn * 32)) return rc;
         if (int rc = lane_fetch(ctx, L, s_out + i0 * 32, o_s, cn * 32)) return rc;
@@ -502,14 +540,15 @@ int plume_sign_batch(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs,
     return PLUME_OK;
 }
 
-int plume_verify_batch(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets,
-                       size_t msg_len, const uint8_t* pk, const uint8_t* nullifier, const uint8_t* c, const uint8_t* s_in,
-                       const uint8_t* r_point, const uint8_t* hashed_to_curve_r, uint8_t* ok) {
+int verify_host(plume_ctx* ctx, int flavour, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                const uint8_t* pk, const uint8_t* nullifier, const uint8_t* c, const uint8_t* s_in, const uint8_t* r_point,
+                const uint8_t* hashed_to_curve_r, uint8_t* ok) {
     if (int rc = check_common(ctx, n, msgs, msg_offsets, msg_len)) return rc;
     if (version != 1 && version != 2) return fail(ctx, PLUME_E_ARG, "version must be 1 or 2");
     if (n == 0) return PLUME_OK;
     if (!pk || !nullifier || !c || !s_in || !ok) return fail(ctx, PLUME_E_ARG, "null array");
-    if (version == 1 && (!r_point || !hashed_to_curve_r)) return fail(ctx, PLUME_E_ARG, "V1 needs r_point and hashed_to_curve_r");
+    const bool need_points = version == 1 || flavour == PLUME_FLAVOUR_ARKWORKS;
+    if (need_points && (!r_point || !hashed_to_curve_r)) return fail(ctx, PLUME_E_ARG, "r_point and hashed_to_curve_r are required");
     ScopedDevice sd(ctx->device);
     size_t k = 0;
     for (size_t i0 = 0; i0 < n; i0 += ctx->chunk, k++) {
@@ -519,15 +558,15 @@ int plume_verify_batch(plume_ctx* ctx, int version, size_t n, const uint8_t* msg
         if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * (64 * 4 + 64 + 1) + 4096)) return rc;
         L.d_io_used = 0;
         L.busy = true;
-        verify_args a;
-        a.version = version; a.n = (uint32_t)cn;
+        verify_args a{};
+        a.version = version; a.flavour = flavour; a.n = (uint32_t)cn;
         if (int rc = lane_msgs(ctx, L, msgs, msg_offsets, msg_len, i0, cn, &a.msgs)) return rc;
         uint8_t *d_pk, *d_nul, *d_c, *d_s, *d_rp = nullptr, *d_hr = nullptr;
         if (int rc = lane_input(ctx, L, pk + i0 * 64, cn * 64, &d_pk)) return rc;
         if (int rc = lane_input(ctx, L, nullifier + i0 * 64, cn * 64, &d_nul)) return rc;
         if (int rc = lane_input(ctx, L, c + i0 * 32, cn * 32, &d_c)) return rc;
         if (int rc = lane_input(ctx, L, s_in + i0 * 32, cn * 32, &d_s)) return rc;
-        if (version == 1) {
+        if (need_points) {
             if (int rc = lane_input(ctx, L, r_point + i0 * 64, cn * 64, &d_rp)) return rc;
             if (int rc = lane_input(ctx, L, hashed_to_curve_r + i0 * 64, cn * 64, &d_hr)) return rc;
         }
@@ -540,6 +579,34 @@ int plume_verify_batch(plume_ctx* ctx, int version, size_t n, const uint8_t* msg
     }
     for (Lane& L : ctx->lanes) if (int rc = lane_finish(ctx, L)) return rc;
     return PLUME_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int plume_sign_batch(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets,
+                     size_t msg_len, const uint8_t* sk, const uint8_t* r, uint8_t* pk, uint8_t* nullifier, uint8_t* c,
+                     uint8_t* s_out, uint8_t* r_point, uint8_t* hashed_to_curve_r, uint8_t* status) {
+    return sign_host(ctx, PLUME_FLAVOUR_K256, version, n, msgs, msg_offsets, msg_len, nullptr, sk, r, pk, nullifier, c, s_out, r_point,
+                     hashed_to_curve_r, status);
+}
+int plume_ark_sign_batch(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                         const uint8_t* pk, const uint8_t* sk, const uint8_t* r, uint8_t* nullifier, uint8_t* digest_private,
+                         uint8_t* s_out, uint8_t* r_point, uint8_t* hashed_to_curve_r, uint8_t* status) {
+    return sign_host(ctx, PLUME_FLAVOUR_ARKWORKS, version, n, msgs, msg_offsets, msg_len, pk, sk, r, nullptr, nullifier, digest_private,
+                     s_out, r_point, hashed_to_curve_r, status);
+}
+int plume_verify_batch(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets,
+                       size_t msg_len, const uint8_t* pk, const uint8_t* nullifier, const uint8_t* c, const uint8_t* s_in,
+                       const uint8_t* r_point, const uint8_t* hashed_to_curve_r, uint8_t* ok) {
+    return verify_host(ctx, PLUME_FLAVOUR_K256, version, n, msgs, msg_offsets, msg_len, pk, nullifier, c, s_in, r_point,
+                       hashed_to_curve_r, ok);
+}
+int plume_ark_verify_batch(plume_ctx* ctx, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                           const uint8_t* pk, const uint8_t* nullifier, const uint8_t* digest_private, const uint8_t* s_in,
+                           const uint8_t* r_point, const uint8_t* hashed_to_curve_r, uint8_t* ok) {
+    return verify_host(ctx, PLUME_FLAVOUR_ARKWORKS, version, n, msgs, msg_offsets, msg_len, pk, nullifier, digest_private, s_in,
+                       r_point, hashed_to_curve_r, ok);
 }
 
 int plume_hash_to_curve_batch(plume_ctx* ctx, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
@@ -655,7 +722,7 @@ int plume_sign_batch_sec1(plume_ctx* ctx, int version, size_t n, const uint8_t* 
         if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * (64 + 64 * 4 + 33 * 4 + 64 + 1) + 8192)) return rc;
         L.d_io_used = 0;
         L.busy = true;
-        sign_args a;
+        sign_args a{};
         a.version = version; a.n = (uint32_t)cn;
         if (int rc = lane_msgs(ctx, L, msgs, msg_offsets, msg_len, i0, cn, &a.msgs)) return rc;
         uint8_t *d_sk, *d_r;
@@ -706,7 +773,7 @@ int plume_verify_batch_sec1(plume_ctx* ctx, int version, size_t n, const uint8_t
         if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * (33 * 4 + 64 * 4 + 64 + 5) + 8192)) return rc;
         L.d_io_used = 0;
         L.busy = true;
-        verify_args a;
+        verify_args a{};
         a.version = version; a.n = (uint32_t)cn;
         if (int rc = lane_msgs(ctx, L, msgs, msg_offsets, msg_len, i0, cn, &a.msgs)) return rc;
         cudaStream_t s = L.stream;

@@ -30,6 +30,11 @@
 #define PLUME_ST_BAD_C 3
 #define PLUME_ST_ZERO_S 4
 #define PLUME_ST_H_INF 5
+#define PLUME_ST_BAD_PK 6
+
+// which reference crate's semantics a batch follows
+#define PLUME_FLAVOUR_K256 0      // rust-k256/: pk derived from sk, c and s are NonZeroScalar (sign rejects c = 0 / c >= n / s = 0)
+#define PLUME_FLAVOUR_ARKWORKS 1  // rust-arkworks/: pk is an input, every scalar is an Fr (zero allowed), c is reduced mod n
 
 // ---- 32-byte element I/O ---------------------------------------------------------------------------
 PLUME_DEV fe ld_fe(const uint32_t* p) {
@@ -198,11 +203,13 @@ enum {
 
 struct sign_args {
     int version;
+    int flavour;          // PLUME_FLAVOUR_*
     uint32_t n;
     msg_view msgs;
     const uint8_t* sk;    // n x 32 BE
     const uint8_t* r;     // n x 32 BE
-    uint8_t* pk;          // n x 64
+    uint8_t* pk;          // n x 64   out (k256 flavour; may be null in the arkworks flavour)
+    const uint8_t* pk_in; // n x 64   in  (arkworks flavour: the keypair's public half, rust-arkworks/src/lib.rs:229-235)
     uint8_t* nullifier;   // n x 64
     uint8_t* c;           // n x 32
     uint8_t* s;           // n x 32
@@ -216,23 +223,6 @@ struct sign_args {
 };
 
 PLUME_DEV sc sc_one() { sc r; for (int i = 0; i < 8; i++) r.v[i] = (i == 0); return r; }
-
-PLUME_DEV void sign_stage_fixed(uint32_t i, const sign_args& a) {
-    sc r = ld_sc_be(a.r + (size_t)i * 32);
-    sc sk = ld_sc_be(a.sk + (size_t)i * 32);
-    uint8_t st = PLUME_ST_OK;
-    if (!sc_is_valid_nonzero(sk)) { st = PLUME_ST_BAD_SK; sk = sc_one(); }
-    if (!sc_is_valid_nonzero(r)) { st = PLUME_ST_BAD_R; r = sc_one(); }
-    a.status[i] = st;
-    jac R = fb_mul(r, a.gtab, a.gw);
-    st_fe(ws_at(a.ws, a.n, WS_AX, i), R.x);
-    st_fe(ws_at(a.ws, a.n, WS_AY, i), R.y);
-    st_fe(ws_at(a.ws, a.n, WS_Z0, i), R.z);
-    jac K = fb_mul(sk, a.gtab, a.gw);
-    st_fe(ws_at(a.ws, a.n, WS_BX, i), K.x);
-    st_fe(ws_at(a.ws, a.n, WS_BY, i), K.y);
-    st_fe(ws_at(a.ws, a.n, WS_Z1, i), K.z);
-}
 
 PLUME_DEV aff ws_load_affine(uint32_t* ws, uint32_t n, int sx, int sy, int sz, uint32_t i) {
     jac p;
@@ -251,6 +241,36 @@ PLUME_DEV void ws_store_jac(uint32_t* ws, uint32_t n, int sx, int sy, int sz, ui
 PLUME_DEV void ws_store_aff(uint32_t* ws, uint32_t n, int sx, int sy, uint32_t i, const aff& p) {
     st_fe(ws_at(ws, n, sx, i), p.x);
     st_fe(ws_at(ws, n, sy, i), p.y);
+}
+
+PLUME_DEV void sign_stage_fixed(uint32_t i, const sign_args& a) {
+    sc r = ld_sc_be(a.r + (size_t)i * 32);
+    sc sk = ld_sc_be(a.sk + (size_t)i * 32);
+    uint8_t st = PLUME_ST_OK;
+    if (a.flavour == PLUME_FLAVOUR_ARKWORKS) {
+        // sign_with_r (rust-arkworks/src/lib.rs:229-278): r and sk are any Fr (zero included), pk comes with the keypair;
+        // hash_to_curve fails on the identity pk (:97-100)
+        if (sc_ge_n(sk)) { st = PLUME_ST_BAD_SK; sk = sc_one(); }
+        if (sc_ge_n(r)) { st = PLUME_ST_BAD_R; r = sc_one(); }
+        aff P;
+        if (!ld_point_be(P, a.pk_in + (size_t)i * 64) || P.inf) { st = PLUME_ST_BAD_PK; P = aff_generator(); }
+        a.status[i] = st;
+        jac R = fb_mul(r, a.gtab, a.gw);
+        ws_store_jac(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i, R);
+        ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, jac_from_aff(P));
+        return;
+    }
+    if (!sc_is_valid_nonzero(sk)) { st = PLUME_ST_BAD_SK; sk = sc_one(); }
+    if (!sc_is_valid_nonzero(r)) { st = PLUME_ST_BAD_R; r = sc_one(); }
+    a.status[i] = st;
+    jac R = fb_mul(r, a.gtab, a.gw);
+    st_fe(ws_at(a.ws, a.n, WS_AX, i), R.x);
+    st_fe(ws_at(a.ws, a.n, WS_AY, i), R.y);
+    st_fe(ws_at(a.ws, a.n, WS_Z0, i), R.z);
+    jac K = fb_mul(sk, a.gtab, a.gw);
+    st_fe(ws_at(a.ws, a.n, WS_BX, i), K.x);
+    st_fe(ws_at(a.ws, a.n, WS_BY, i), K.y);
+    st_fe(ws_at(a.ws, a.n, WS_Z1, i), K.z);
 }
 
 PLUME_DEV void sign_stage_h2c(uint32_t i, const sign_args& a) {
@@ -282,8 +302,9 @@ PLUME_DEV void sign_stage_varbase(uint32_t i, const sign_args& a, const Tab& tab
     fe zg = vb_build_table(h.x, h.y, tab);
     sc r = ld_sc_be(a.r + (size_t)i * 32);
     sc sk = ld_sc_be(a.sk + (size_t)i * 32);
-    if (!sc_is_valid_nonzero(sk)) sk = sc_one();
-    if (!sc_is_valid_nonzero(r)) r = sc_one();
+    const bool zero_ok = a.flavour == PLUME_FLAVOUR_ARKWORKS;   // an Fr may be zero: h^0 is the identity
+    if (sc_ge_n(sk) || (!zero_ok && sc_is_zero(sk))) sk = sc_one();
+    if (sc_ge_n(r) || (!zero_ok && sc_is_zero(r))) r = sc_one();
 #pragma unroll 1
     for (int which = 0; which < 2; which++) {
         jac o = vb_mul_tab(which == 0 ? r : sk, tab, zg);
@@ -292,17 +313,36 @@ PLUME_DEV void sign_stage_varbase(uint32_t i, const sign_args& a, const Tab& tab
     }
 }
 
+// affine point read back from two workspace slots: (0, 0) is how the identity was stored (no curve point has y = 0)
+PLUME_DEV aff ws_load_aff_xy(uint32_t* ws, uint32_t n, int sx, int sy, uint32_t i) {
+    aff p;
+    p.x = ld_fe(ws_at(ws, n, sx, i));
+    p.y = ld_fe(ws_at(ws, n, sy, i));
+    uint32_t o = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) o |= p.x.v[k] | p.y.v[k];
+    p.inf = (o == 0);
+    return p;
+}
+
 PLUME_DEV void sign_stage_final(uint32_t i, const sign_args& a) {
     aff z = ws_load_affine(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i);
     aff nul = ws_load_affine(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i);
-    aff h, R, K;
-    h.x = ld_fe(ws_at(a.ws, a.n, WS_HX, i)); h.y = ld_fe(ws_at(a.ws, a.n, WS_HY, i)); h.inf = 0;
-    R.x = ld_fe(ws_at(a.ws, a.n, WS_RX, i)); R.y = ld_fe(ws_at(a.ws, a.n, WS_RY, i)); R.inf = 0;
-    K.x = ld_fe(ws_at(a.ws, a.n, WS_KX, i)); K.y = ld_fe(ws_at(a.ws, a.n, WS_KY, i)); K.inf = 0;
+    aff h = ws_load_aff_xy(a.ws, a.n, WS_HX, WS_HY, i);
+    aff R = ws_load_aff_xy(a.ws, a.n, WS_RX, WS_RY, i);   // the identity only in the arkworks flavour (r = 0)
+    aff K = ws_load_aff_xy(a.ws, a.n, WS_KX, WS_KY, i);
     uint8_t st = a.status[i];
     sc c = plume_challenge(a.version, K, h, nul, R, z);
     sc s = sc_one();
-    if (st == PLUME_ST_OK) {
+    if (a.flavour == PLUME_FLAVOUR_ARKWORKS) {
+        // c = Fr::from_be_bytes_mod_order(digest); s = r + sk * c, nothing is rejected (rust-arkworks/src/lib.rs:257-262)
+        c = sc_reduce256(c);
+        if (st == PLUME_ST_OK) {
+            sc r = ld_sc_be(a.r + (size_t)i * 32);
+            sc sk = ld_sc_be(a.sk + (size_t)i * 32);
+            s = sc_add(r, sc_mul(c, sk));
+        }
+    } else if (st == PLUME_ST_OK) {
         if (!sc_is_valid_nonzero(c)) {
             st = PLUME_ST_BAD_C;  // NonZeroScalar::from_repr(c).expect (randomizedsigner.rs:90-91)
         } else {
@@ -315,7 +355,7 @@ PLUME_DEV void sign_stage_final(uint32_t i, const sign_args& a) {
     a.status[i] = st;
     const bool ok = (st == PLUME_ST_OK);
     aff none = aff_infinity();
-    st_point_be(a.pk + (size_t)i * 64, ok ? K : none);
+    if (a.pk) st_point_be(a.pk + (size_t)i * 64, ok ? K : none);
     st_point_be(a.nullifier + (size_t)i * 64, ok ? nul : none);
     if (ok) { st_sc_be(a.c + (size_t)i * 32, c); st_sc_be(a.s + (size_t)i * 32, s); }
     else { st_zero32(a.c + (size_t)i * 32); st_zero32(a.s + (size_t)i * 32); }
@@ -352,6 +392,7 @@ PLUME_DEV void binv_body(uint32_t t, uint32_t T, uint32_t* Z, uint32_t* scratch,
 // ---- verify -----------------------------------------------------------------------------------------------
 struct verify_args {
     int version;
+    int flavour;               // PLUME_FLAVOUR_*; arkworks = verify_non_zk (rust-arkworks/src/tests.rs:28-78)
     uint32_t n;
     msg_view msgs;
     const uint8_t* pk;         // n x 64
@@ -373,8 +414,10 @@ PLUME_DEV void verify_stage_h2c(uint32_t i, const verify_args& a) {
     bool good = ld_point_be(pk, a.pk + (size_t)i * 64);
     good = ld_point_be(nul, a.nullifier + (size_t)i * 64) && good;
     sc c = ld_sc_be(a.c + (size_t)i * 32), s = ld_sc_be(a.s + (size_t)i * 32);
-    good = good && sc_is_valid_nonzero(c) && sc_is_valid_nonzero(s);  // NonZeroScalar fields
-    if (a.version == 1) {
+    const bool ark = a.flavour == PLUME_FLAVOUR_ARKWORKS;
+    if (ark) good = good && !sc_ge_n(c) && !sc_ge_n(s) && !pk.inf;   // Fr fields (zero allowed); hash_to_curve fails on pk = identity
+    else good = good && sc_is_valid_nonzero(c) && sc_is_valid_nonzero(s);  // NonZeroScalar fields
+    if (a.version == 1 || ark) {   // the arkworks signature always carries r_point and hashed_to_curve_r
         aff t;
         good = ld_point_be(t, a.r_point + (size_t)i * 64) && good;
         good = ld_point_be(t, a.hashed_to_curve_r + (size_t)i * 64) && good;
@@ -489,7 +532,7 @@ PLUME_DEV void verify_stage_final(uint32_t i, const verify_args& a) {
     aff pk, nul;
     ld_point_be(pk, a.pk + (size_t)i * 64);
     ld_point_be(nul, a.nullifier + (size_t)i * 64);
-    if (a.version == 1) {
+    if (a.version == 1 || a.flavour == PLUME_FLAVOUR_ARKWORKS) {   // verify_non_zk compares both points in V2 as well
         aff rs, zs;
         ld_point_be(rs, a.r_point + (size_t)i * 64);
         ld_point_be(zs, a.hashed_to_curve_r + (size_t)i * 64);

@@ -164,6 +164,30 @@ class PlumeContext:
         self._check(rc, "plume_verify_batch")
         return ok
 
+    # ---- arkworks flavour (rust-arkworks/src/lib.rs:229-278, tests.rs:28-78) -----------------------------
+    def ark_sign_batch(self, version, msgs, pk, sk, r):
+        """plume_ark_sign_batch.  pk: u8[n,64] (input); sk, r: u8[n,32] big-endian Fr (zero allowed)."""
+        blob, offs, mlen, n = self._msgs(msgs, None)
+        pk = _as_u8(pk, (n, 64)); sk = _as_u8(sk, (n, 32)); r = _as_u8(r, (n, 32))
+        o = {k: np.empty((n, w), dtype=np.uint8) for k, w in
+             (("nullifier", 64), ("digest_private", 32), ("s", 32), ("r_point", 64), ("hashed_to_curve_r", 64))}
+        o["status"] = np.empty(n, dtype=np.uint8)
+        rc = self._lib.plume_ark_sign_batch(self._h, version, n, _ptr(blob), _ptr(offs), mlen, _ptr(pk), _ptr(sk), _ptr(r),
+                                            _ptr(o["nullifier"]), _ptr(o["digest_private"]), _ptr(o["s"]), _ptr(o["r_point"]),
+                                            _ptr(o["hashed_to_curve_r"]), _ptr(o["status"]))
+        self._check(rc, "plume_ark_sign_batch")
+        return o
+
+    def ark_verify_batch(self, version, msgs, pk, nullifier, digest_private, s, r_point, hashed_to_curve_r):
+        blob, offs, mlen, n = self._msgs(msgs, None)
+        a = [_as_u8(x, (n, w)) for x, w in ((pk, 64), (nullifier, 64), (digest_private, 32), (s, 32), (r_point, 64),
+                                             (hashed_to_curve_r, 64))]
+        ok = np.empty(n, dtype=np.uint8)
+        rc = self._lib.plume_ark_verify_batch(self._h, version, n, _ptr(blob), _ptr(offs), mlen, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]),
+                                              _ptr(a[3]), _ptr(a[4]), _ptr(a[5]), _ptr(ok))
+        self._check(rc, "plume_ark_verify_batch")
+        return ok
+
     # ---- SEC1-compressed wire form (33-byte slots) ----------------------------------------------------
     def points_compress(self, pts64):
         a = _as_u8(pts64); n = a.size // 64; a = a.reshape(n, 64)
