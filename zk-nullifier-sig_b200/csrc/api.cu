@@ -43,7 +43,8 @@ struct plume_ctx {
     int device = 0;
     int gw = 0;
     uint32_t* gtab = nullptr;
-    size_t chunk = 0;
+    size_t chunk = 0;        // capacity of the workspaces: largest n of one pass
+    size_t host_chunk = 0;   // pipelining granularity of the host-pointer entry points
     uint32_t binv_k = 16;
     Lane lanes[2];
     std::string err;
@@ -286,7 +287,14 @@ int plume_ctx_create(plume_ctx** out, int device, int fixed_window_bits) {
     plume_ctx* c = new plume_ctx();
     c->device = device;
     c->gw = w;
-    c->chunk = env_size("PLUME_CHUNK_ITEMS", (size_t)1 << 19);  // 4096 blocks = 6.9 waves of 148 SMs x 4 blocks: 1 % tail
+    // capacity of one pass (what the `_device` entry points accept): large, so that a device-resident batch is one launch
+    // per stage with a negligible tail
+    c->chunk = env_size("PLUME_CHUNK_ITEMS", (size_t)1 << 20);
+    // granularity of the host-pointer entry points: 3 full waves of the kernels that hold 4 blocks of 128 threads per SM
+    // = 4 full waves of the one that holds 3 (k_verify_mul_b), i.e. no tail, and short enough that the first upload and
+    // the last download of a call -- the part the two lanes cannot overlap -- are a small fraction of it
+    c->host_chunk = env_size("PLUME_HOST_CHUNK_ITEMS", (size_t)prop.multiProcessorCount * 128 * 12);
+    if (c->host_chunk > c->chunk) c->host_chunk = c->chunk;
     c->binv_k = (uint32_t)env_size("PLUME_BINV_K", 16);
     struct Guard { plume_ctx* c; ~Guard() { if (c) plume_ctx_destroy(c); } } guard{c};
     for (Lane& L : c->lanes) {
@@ -503,8 +511,8 @@ int sign_host(plume_ctx* ctx, int flavour, int version, size_t n, const uint8_t*
     if (flavour == PLUME_FLAVOUR_ARKWORKS ? !pk_in : !pk) return fail(ctx, PLUME_E_ARG, "null pk array");
     ScopedDevice sd(ctx->device);
     size_t k = 0;
-    for (size_t i0 = 0; i0 < n; i0 += ctx->chunk, k++) {
-        const size_t cn = (n - i0 < ctx->chunk) ? n - i0 : ctx->chunk;
+    for (size_t i0 = 0; i0 < n; i0 += ctx->host_chunk, k++) {
+        const size_t cn = (n - i0 < ctx->host_chunk) ? n - i0 : ctx->host_chunk;
         Lane& L = ctx->lanes[k & 1];
         if (int rc = lane_finish(ctx, L)) return rc;
         if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * (64 + 64 * 4 + 64 + 1) + 4096)) return rc;
@@ -551,8 +559,8 @@ int verify_host(plume_ctx* ctx, int flavour, int version, size_t n, const uint8_
     if (need_points && (!r_point || !hashed_to_curve_r)) return fail(ctx, PLUME_E_ARG, "r_point and hashed_to_curve_r are required");
     ScopedDevice sd(ctx->device);
     size_t k = 0;
-    for (size_t i0 = 0; i0 < n; i0 += ctx->chunk, k++) {
-        const size_t cn = (n - i0 < ctx->chunk) ? n - i0 : ctx->chunk;
+    for (size_t i0 = 0; i0 < n; i0 += ctx->host_chunk, k++) {
+        const size_t cn = (n - i0 < ctx->host_chunk) ? n - i0 : ctx->host_chunk;
         Lane& L = ctx->lanes[k & 1];
         if (int rc = lane_finish(ctx, L)) return rc;
         if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * (64 * 4 + 64 + 1) + 4096)) return rc;
@@ -616,8 +624,8 @@ int plume_hash_to_curve_batch(plume_ctx* ctx, size_t n, const uint8_t* msgs, con
     if (!out) return fail(ctx, PLUME_E_ARG, "null array");
     ScopedDevice sd(ctx->device);
     size_t k = 0;
-    for (size_t i0 = 0; i0 < n; i0 += ctx->chunk, k++) {
-        const size_t cn = (n - i0 < ctx->chunk) ? n - i0 : ctx->chunk;
+    for (size_t i0 = 0; i0 < n; i0 += ctx->host_chunk, k++) {
+        const size_t cn = (n - i0 < ctx->host_chunk) ? n - i0 : ctx->host_chunk;
         Lane& L = ctx->lanes[k & 1];
         if (int rc = lane_finish(ctx, L)) return rc;
         if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * 64 + 4096)) return rc;
@@ -660,8 +668,8 @@ int plume_points_compress_batch(plume_ctx* ctx, size_t n, const uint8_t* in64, u
     if (!in64 || !out33) return fail(ctx, PLUME_E_ARG, "null array");
     ScopedDevice sd(ctx->device);
     size_t k = 0;
-    for (size_t i0 = 0; i0 < n; i0 += ctx->chunk, k++) {
-        const size_t cn = (n - i0 < ctx->chunk) ? n - i0 : ctx->chunk;
+    for (size_t i0 = 0; i0 < n; i0 += ctx->host_chunk, k++) {
+        const size_t cn = (n - i0 < ctx->host_chunk) ? n - i0 : ctx->host_chunk;
         Lane& L = ctx->lanes[k & 1];
         if (int rc = lane_finish(ctx, L)) return rc;
         if (int rc = lane_reserve(ctx, L, cn * 97 + 4096)) return rc;
@@ -685,8 +693,8 @@ int plume_points_decompress_batch(plume_ctx* ctx, size_t n, const uint8_t* in33,
     if (!in33 || !out64 || !ok) return fail(ctx, PLUME_E_ARG, "null array");
     ScopedDevice sd(ctx->device);
     size_t k = 0;
-    for (size_t i0 = 0; i0 < n; i0 += ctx->chunk, k++) {
-        const size_t cn = (n - i0 < ctx->chunk) ? n - i0 : ctx->chunk;
+    for (size_t i0 = 0; i0 < n; i0 += ctx->host_chunk, k++) {
+        const size_t cn = (n - i0 < ctx->host_chunk) ? n - i0 : ctx->host_chunk;
         Lane& L = ctx->lanes[k & 1];
         if (int rc = lane_finish(ctx, L)) return rc;
         if (int rc = lane_reserve(ctx, L, cn * 98 + 4096)) return rc;
@@ -715,8 +723,8 @@ int plume_sign_batch_sec1(plume_ctx* ctx, int version, size_t n, const uint8_t* 
     if (!sk || !r || !pk33 || !nullifier33 || !c || !s_out || !status) return fail(ctx, PLUME_E_ARG, "null array");
     ScopedDevice sd(ctx->device);
     size_t k = 0;
-    for (size_t i0 = 0; i0 < n; i0 += ctx->chunk, k++) {
-        const size_t cn = (n - i0 < ctx->chunk) ? n - i0 : ctx->chunk;
+    for (size_t i0 = 0; i0 < n; i0 += ctx->host_chunk, k++) {
+        const size_t cn = (n - i0 < ctx->host_chunk) ? n - i0 : ctx->host_chunk;
         Lane& L = ctx->lanes[k & 1];
         if (int rc = lane_finish(ctx, L)) return rc;
         if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * (64 + 64 * 4 + 33 * 4 + 64 + 1) + 8192)) return rc;
@@ -766,8 +774,8 @@ int plume_verify_batch_sec1(plume_ctx* ctx, int version, size_t n, const uint8_t
     if (version == 1 && (!r_point33 || !hashed_to_curve_r33)) return fail(ctx, PLUME_E_ARG, "V1 needs r_point and hashed_to_curve_r");
     ScopedDevice sd(ctx->device);
     size_t k = 0;
-    for (size_t i0 = 0; i0 < n; i0 += ctx->chunk, k++) {
-        const size_t cn = (n - i0 < ctx->chunk) ? n - i0 : ctx->chunk;
+    for (size_t i0 = 0; i0 < n; i0 += ctx->host_chunk, k++) {
+        const size_t cn = (n - i0 < ctx->host_chunk) ? n - i0 : ctx->host_chunk;
         Lane& L = ctx->lanes[k & 1];
         if (int rc = lane_finish(ctx, L)) return rc;
         if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * (33 * 4 + 64 * 4 + 64 + 5) + 8192)) return rc;
