@@ -23,11 +23,11 @@ for rep in range(3):
     o = ctx.sign_batch(1, msgs, sk, r)
     ok = ctx.verify_batch(1, msgs, o["pk"], o["nullifier"], o["c"], o["s"], o["r_point"], o["hashed_to_curve_r"])
 for st in ("sign_fixed", "sign_h2c", "sign_varbase", "sign_final", "verify_h2c", "verify_muls", "verify_mul_a", "verify_mul_b", "verify_final", "binv"):
-    ms, k = ctx.stage_ms(st); res[st] = round(ms / max(k, 1), 3)
+    ms, k = ctx.stage_ms(st); res[st] = round(ms / 3, 3)          # per batch of n items (3 timed repetitions)
 res["verify_muls"] = round(res["verify_muls"] + res["verify_mul_a"] + res["verify_mul_b"], 3)
-res["sign_ms"] = round(res["sign_fixed"] + res["sign_h2c"] + res["sign_varbase"] + res["sign_final"] + 3 * res["binv"], 3)
-res["verify_ms"] = round(res["verify_h2c"] + res["verify_muls"] + res["verify_final"] + 2 * res["binv"], 3)
-res["sign_per_s"] = round(min(n, ctx.chunk_items) / res["sign_ms"] * 1e3); res["verify_per_s"] = round(min(n, ctx.chunk_items) / res["verify_ms"] * 1e3)
+res["sign_ms"] = round(res["sign_fixed"] + res["sign_h2c"] + res["sign_varbase"] + res["sign_final"] + res["binv"] * 3 / 5, 3)
+res["verify_ms"] = round(res["verify_h2c"] + res["verify_muls"] + res["verify_final"] + res["binv"] * 2 / 5, 3)
+res["sign_per_s"] = round(n / res["sign_ms"] * 1e3); res["verify_per_s"] = round(n / res["verify_ms"] * 1e3)
 m = 256
 want = c_oracle.sign_batch(1, msgs[:m], sk[:m], r[:m], threads=16)
 res["bit_exact"] = bool(all(np.array_equal(o[k][:m], want[k]) for k in want)) and bool(ok.all())

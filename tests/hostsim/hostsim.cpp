@@ -99,6 +99,16 @@ void hs_vb_mul(const uint8_t* p64, const uint8_t* k32, uint8_t* out64) {
     aff q = r.inf ? aff_infinity() : aff_from_jac_zinv(r, fe_inv(r.z));
     st_point_be(out64, q);
 }
+void hs_comb_mul(const uint8_t* p64, const uint8_t* k32, uint8_t* out64) {
+    aff p; ld_point_be(p, p64);
+    sc k = ld_sc_be(k32);
+    uint32_t area[COMB_AREA_WORDS];
+    fe zg = comb_build_table(p.x, p.y, area);
+    fe zg2 = fe_sqr(zg);
+    jac r = comb_mul_tab(k, area, zg, fe_mul(p.x, zg2), fe_mul(p.y, fe_mul(zg2, zg)));
+    aff q = r.inf ? aff_infinity() : aff_from_jac_zinv(r, fe_inv(r.z));
+    st_point_be(out64, q);
+}
 void hs_fb_mul(const uint8_t* k32, int w, uint8_t* out64) {
     build_gtab(w);
     sc k = ld_sc_be(k32);
@@ -108,7 +118,8 @@ void hs_fb_mul(const uint8_t* k32, int w, uint8_t* out64) {
 }
 
 // flavour 0: k256 (pk is an output), 1: arkworks (pk is an input)
-int hs_sign_batch(int flavour, int version, uint32_t n, const uint8_t* msgs, const uint64_t* offs, uint32_t msg_len,
+// comb != 0: the shipped signed-comb form of the variable-base stage; 0: the windowed ladder (both table layouts)
+int hs_sign_batch(int flavour, int comb, int version, uint32_t n, const uint8_t* msgs, const uint64_t* offs, uint32_t msg_len,
                   const uint8_t* sk, const uint8_t* r, uint8_t* pk, uint8_t* nul, uint8_t* c, uint8_t* s,
                   uint8_t* r_point, uint8_t* hr, uint8_t* status, int gw, uint32_t binv_threads) {
     build_gtab(gw);
@@ -125,7 +136,8 @@ int hs_sign_batch(int flavour, int version, uint32_t n, const uint8_t* msgs, con
     run_binv(a.ws, n, n, binv_threads);
     // alternate between the two table layouts the kernels can use
     for (uint32_t i = 0; i < n; i++) {
-        if (i & 1) sign_stage_varbase(i, a, vb_tab_linear{tabw});
+        if (comb) sign_stage_varbase_comb(i, a, tabw);
+        else if (i & 1) sign_stage_varbase(i, a, vb_tab_linear{tabw});
         else sign_stage_varbase(i, a, vb_tab_strided{tabw + (i & 3), 4});
     }
     run_binv(a.ws, n, 2 * n, binv_threads);

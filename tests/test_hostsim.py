@@ -106,6 +106,19 @@ def test_map_to_curve_and_scalar_muls():
     assert bytes(out) == bytes(64)
 
 
+def test_signed_comb_scalar_multiplication():
+    """mul.cuh comb_*: k * P through the signed comb the signer uses for h^r and h^sk (teeth shared between scalars);
+    odd and even magnitudes, zero, the GLV edge values, and scalars whose halves are tiny or maximal."""
+    rnd = random.Random(12)
+    ks = [0, 1, 2, 3, 4, N - 1, N - 2, 2**32, 2**33, 2**33 - 1, 2**66, 2**99 + 1, 2**128, 2**131 % N, LAMBDA, LAMBDA + 1, N - LAMBDA,
+          (LAMBDA * 2) % N, 0xFFFFFFFF, 2**255 % N] + [rnd.randrange(N) for _ in range(40)]
+    for t, k in enumerate(ks):
+        base = c_oracle.mul_g(rnd.randrange(1, N)) if t % 3 else _pt64(R.G)
+        out = (ctypes.c_uint8 * 64)()
+        H.lib().hs_comb_mul(base, k.to_bytes(32, "big"), out)
+        assert bytes(out) == (c_oracle.mul(base, k) if k else bytes(64)), hex(k)
+
+
 def test_h2c_pipeline(golden):
     msgs = [b"abc", b"", bytes(golden["h2c_preimage62"]["preimage"])] + [bytes([i]) * i for i in (1, 54, 55, 56, 63, 64, 65, 127, 128, 200)]
     out = H.h2c_batch(msgs)
@@ -115,10 +128,11 @@ def test_h2c_pipeline(golden):
 
 def _check_sign_verify(ver, msgs, sks, rs, golden=None):
     skb = b"".join(x.to_bytes(32, "big") for x in sks); rb = b"".join(x.to_bytes(32, "big") for x in rs)
-    got = H.sign_batch(ver, msgs, skb, rb, gw=8, binv_threads=5)
     want = c_oracle.sign_batch(ver, msgs, skb, rb, threads=2)
-    for k in ("status", "pk", "nullifier", "c", "s", "r_point", "hashed_to_curve_r"):
-        assert np.array_equal(got[k], want[k]), k
+    for comb in (True, False):   # the shipped signed comb, and the windowed ladder kept for the shared-memory build
+        got = H.sign_batch(ver, msgs, skb, rb, gw=8, binv_threads=5, comb=comb)
+        for k in ("status", "pk", "nullifier", "c", "s", "r_point", "hashed_to_curve_r"):
+            assert np.array_equal(got[k], want[k]), (k, comb)
     return got
 
 

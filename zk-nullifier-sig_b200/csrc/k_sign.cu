@@ -12,7 +12,11 @@ __global__ void __launch_bounds__(128, PLUME_H2C_MINBLOCKS) k_sign_h2c(sign_args
 __global__ void __launch_bounds__(VB_BLOCK, PLUME_VB_MINBLOCKS) k_sign_varbase(sign_args a) {
     extern __shared__ uint32_t vb_smem[];
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < a.n) sign_stage_varbase(i, a, VB_TAB(a, i));
+#if defined(PLUME_VB_TAB_SMEM) || defined(PLUME_SIGN_WINDOWED)
+    if (i < a.n) sign_stage_varbase(i, a, VB_TAB(a, i));          // windowed ladder per scalar (132 doublings each)
+#else
+    if (i < a.n) sign_stage_varbase_comb(i, a, a.vbtab + (size_t)i * COMB_AREA_WORDS);   // signed comb, shared teeth
+#endif
 }
 __global__ void __launch_bounds__(128) k_sign_final(sign_args a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

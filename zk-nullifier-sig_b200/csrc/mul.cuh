@@ -215,3 +215,169 @@ PLUME_DEV fe vb_build_table_pair(const fe& p1x, const fe& p1y, const Tab& tab1, 
     }
     return fe_mul(z1, z2);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Signed comb for SEVERAL scalars on ONE variable base (the signer's h^r and h^sk).
+//
+// With teeth at 2^(33 j), j = 0..3, a 132-bit odd magnitude m = sum_i b_i 2^i with every b_i in {-1, +1}
+// (b_i = +1 iff bit i+1 of m is set, b_131 = +1) is  sum_{c=0..32} 2^c * (b_c T0 + b_{c+33} T1 + b_{c+66} T2 + b_{c+99} T3)
+// with T_j = 2^(33 j) P: 33 doublings and 33 additions of a table entry  +-(T3 +- T2 +- T1 +- T0)  per half-scalar,
+// the 99 doublings that produce T1..T3 being paid ONCE for all scalars on this base.  Two scalars with GLV halves:
+// 99 + 2*33 doublings and 4*33 additions instead of 2*132 doublings and 4*33 additions of the windowed ladder.
+// The eight entries (T3 positive) are brought to a common denominator Zg like the window table above, so the main
+// loop uses mixed additions and the result's Z is multiplied by Zg at the end.  An even magnitude is made odd by
+// adding one, and the base is subtracted again at the end.
+//
+// Storage (global scratch, 256 words per item): words 0..127 the table (entry e: x at 16e, y at 16e+8), words
+// 128..191 beta * x of every entry (the endomorphism of the second GLV half, so no multiplication per addition),
+// words 192..255 scratch for T1, T2 while the chain runs.
+// ---------------------------------------------------------------------------------------------
+#define COMB_TEETH_BITS 33
+#define COMB_AREA_WORDS 256
+
+PLUME_DEV void comb_st_fe(uint32_t* p, const fe& a) {
+#ifdef PLUME_HOSTSIM
+    for (int i = 0; i < 8; i++) p[i] = a.v[i];
+#else
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    q[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+#endif
+}
+PLUME_DEV fe comb_ld_fe(const uint32_t* p) {
+    fe r;
+#ifdef PLUME_HOSTSIM
+    for (int i = 0; i < 8; i++) r.v[i] = p[i];
+#else
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+#endif
+    return r;
+}
+PLUME_DEV void comb_st_jac(uint32_t* p, const jac& a) { comb_st_fe(p, a.x); comb_st_fe(p + 8, a.y); comb_st_fe(p + 16, a.z); }
+PLUME_DEV jac comb_ld_jac(const uint32_t* p) { jac r; r.x = comb_ld_fe(p); r.y = comb_ld_fe(p + 8); r.z = comb_ld_fe(p + 16); r.inf = 0; return r; }
+
+// Builds the table for the affine, on-curve, non-identity point (px, py) of prime order; returns Zg.
+PLUME_DEV fe comb_build_table(const fe& px, const fe& py, uint32_t* area) {
+    uint32_t* tmp = area + 192;
+    jac cur;
+    cur.x = px; cur.y = py; cur.z = fe_one(); cur.inf = 0;
+#pragma unroll 1
+    for (int j = 1; j <= 3; j++) {
+#pragma unroll 1
+        for (int i = 0; i < COMB_TEETH_BITS; i++) cur = jac_dbl(cur);
+        if (j < 3) comb_st_jac(tmp + (j - 1) * 24, cur);   // T1, T2
+    }
+    // cur = T3.  lo[q]: q = 0: -(T1 + T0), 1: -(T1 - T0) , 2: T1 - T0, 3: T1 + T0   (index = t1 t0, t = "same sign as T3")
+    // entries: e = t2 t1 t0:  T3 + (t2 ? T2 : -T2) + lo[t1 t0]
+    jac t2p = comb_ld_jac(tmp + 24);
+    jac hi1 = jac_add(cur, t2p);            // T3 + T2
+    jac hi0 = jac_add(cur, jac_neg(t2p));   // T3 - T2
+    jac t1p = comb_ld_jac(tmp);
+    jac s = jac_add_aff(t1p, px, py, 0);                    // T1 + T0
+    jac d = jac_add_aff(t1p, px, fe_neg(py), 0);            // T1 - T0
+    // the four low combinations live in the scratch area (T1, T2 are dead now): 4 x 24 words = words 192..255 + 32 words
+    // of the beta area, which is written last
+    uint32_t* lo = area + 160;
+    comb_st_jac(lo + 0 * 24, jac_neg(s));
+    comb_st_jac(lo + 1 * 24, jac_neg(d));
+    comb_st_jac(lo + 2 * 24, d);
+    comb_st_jac(lo + 3 * 24, s);
+    // entries as Jacobian points: x, y into the table, z kept in local memory for the common-denominator pass
+    fe zs[8];
+#pragma unroll 1
+    for (int e = 0; e < 8; e++) {
+        jac l = comb_ld_jac(lo + (e & 3) * 24);
+        jac r = jac_add((e & 4) ? hi1 : hi0, l);
+        comb_st_fe(area + e * 16, r.x);
+        comb_st_fe(area + e * 16 + 8, r.y);
+        zs[e] = r.z;
+    }
+    // common denominator Zg = z0 z1 ... z7: entry e is scaled by f = Zg / z_e (x f^2, y f^3)
+    fe pre[8];                              // pre[e] = z0 ... z_{e-1}
+    fe acc = fe_one();
+#pragma unroll 1
+    for (int e = 0; e < 8; e++) { pre[e] = acc; acc = fe_mul(acc, zs[e]); }
+    fe zg = acc;
+    fe suf = fe_one();                      // z_{e+1} ... z7
+    const fe beta = ec_beta();
+#pragma unroll 1
+    for (int e = 7; e >= 0; e--) {
+        fe f = fe_mul(pre[e], suf);
+        suf = fe_mul(suf, zs[e]);
+        fe f2 = fe_sqr(f);
+        fe x = fe_mul(comb_ld_fe(area + e * 16), f2);
+        fe y = fe_mul(comb_ld_fe(area + e * 16 + 8), fe_mul(f2, f));
+        comb_st_fe(area + e * 16, x);
+        comb_st_fe(area + e * 16 + 8, y);
+    }
+#pragma unroll 1
+    for (int e = 0; e < 8; e++) comb_st_fe(area + 128 + e * 8, fe_mul(comb_ld_fe(area + e * 16), beta));
+    return zg;
+}
+
+// rows of the signed-digit matrix of one half-scalar: bit c of row[j] = 1 iff b_{c + 33 j} = +1
+struct comb_rows { uint64_t row[4]; uint32_t neg; uint32_t even; };
+PLUME_DEV comb_rows comb_recode(const glv_half& h) {
+    // m' = m | 1 (m + 1 when m is even); digits from m'' = (m' >> 1) | 2^131
+    uint32_t w[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) w[i] = h.mag[i];
+    comb_rows r;
+    r.even = (w[0] & 1) ^ 1;
+    r.neg = h.neg;
+#pragma unroll
+    for (int i = 0; i < 4; i++) w[i] = (w[i] >> 1) | (w[i + 1] << 31);
+    w[4] = (w[4] >> 1) | (1u << 3);        // bit 131 = bit 3 of word 4
+    // row j = bits [33 j, 33 j + 33)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int lo = COMB_TEETH_BITS * j, wi = lo >> 5, sh = lo & 31;
+        uint64_t v = ((uint64_t)w[wi] >> sh);
+        if (wi + 1 < 5) v |= (uint64_t)w[wi + 1] << (32 - sh);
+        if (wi + 2 < 5 && sh != 0) v |= (uint64_t)w[wi + 2] << (64 - sh);
+        r.row[j] = v & ((1ull << COMB_TEETH_BITS) - 1);
+    }
+    return r;
+}
+
+// acc += (digit column c of rows) * table, on the second GLV half with the beta-twisted x
+PLUME_DEV jac comb_add_column(const jac& acc, const comb_rows& r, int c, bool endo, const uint32_t* area) {
+    uint32_t s0 = (uint32_t)(r.row[0] >> c) & 1, s1 = (uint32_t)(r.row[1] >> c) & 1, s2 = (uint32_t)(r.row[2] >> c) & 1,
+             s3 = (uint32_t)(r.row[3] >> c) & 1;
+    uint32_t e = ((s2 == s3) << 2) | ((s1 == s3) << 1) | (s0 == s3);
+    uint32_t neg = (s3 ^ 1) ^ r.neg;
+    fe x = comb_ld_fe(endo ? area + 128 + e * 8 : area + e * 16);
+    fe y = comb_ld_fe(area + e * 16 + 8);
+    fe ny = fe_neg(y);
+    y = fe_cmov(y, ny, neg != 0);
+    return jac_add_aff(acc, x, y, 0);
+}
+
+// k * P from the prepared comb table; k canonical in [0, n); (px, py) = P on the isomorphic curve is entry-free: the
+// parity correction needs P itself, expressed with the table's denominator: P' = (px zg^2, py zg^3)
+PLUME_DEV jac comb_mul_tab(const sc& k, const uint32_t* area, const fe& zg, const fe& pxs, const fe& pys) {
+    glv_half h1, h2;
+    glv_split(k, h1, h2);
+    comb_rows r1 = comb_recode(h1), r2 = comb_recode(h2);
+    jac acc = jac_infinity();
+#pragma unroll 1
+    for (int c = COMB_TEETH_BITS - 1; c >= 0; c--) {
+        acc = jac_dbl(acc);
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) acc = comb_add_column(acc, h ? r2 : r1, c, h != 0, area);
+    }
+    // undo the "+ 1" of the even magnitudes: subtract sign * P (first half) / sign * beta(P) (second half)
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+        const comb_rows& r = h ? r2 : r1;
+        if (r.even) {
+            fe x = h ? fe_mul(pxs, ec_beta()) : pxs;
+            fe y = r.neg ? pys : fe_neg(pys);     // subtracting (+P) when the half is positive
+            acc = jac_add_aff(acc, x, y, 0);
+        }
+    }
+    if (!acc.inf) acc.z = fe_mul(acc.z, zg);
+    return acc;
+}

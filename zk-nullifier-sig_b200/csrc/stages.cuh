@@ -313,6 +313,34 @@ PLUME_DEV void sign_stage_varbase(uint32_t i, const sign_args& a, const Tab& tab
     }
 }
 
+// The same stage with the signed comb (mul.cuh): the 99 doublings that build the teeth are shared by h^r and h^sk.
+// `area`: COMB_AREA_WORDS words of this thread's global scratch.
+PLUME_DEV void sign_stage_varbase_comb(uint32_t i, const sign_args& a, uint32_t* area) {
+    aff h = ws_load_affine(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i);
+    ws_store_aff(a.ws, a.n, WS_HX, WS_HY, i, h);
+    if (h.inf) {
+        a.status[i] = PLUME_ST_H_INF;   // the reference panics here (randomizedsigner.rs:61)
+        jac o = jac_infinity();
+        ws_store_jac(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i, o);
+        ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, o);
+        return;
+    }
+    fe zg = comb_build_table(h.x, h.y, area);
+    fe zg2 = fe_sqr(zg);
+    fe hxs = fe_mul(h.x, zg2), hys = fe_mul(h.y, fe_mul(zg2, zg));   // h on the table's isomorphic curve
+    sc r = ld_sc_be(a.r + (size_t)i * 32);
+    sc sk = ld_sc_be(a.sk + (size_t)i * 32);
+    const bool zero_ok = a.flavour == PLUME_FLAVOUR_ARKWORKS;
+    if (sc_ge_n(sk) || (!zero_ok && sc_is_zero(sk))) sk = sc_one();
+    if (sc_ge_n(r) || (!zero_ok && sc_is_zero(r))) r = sc_one();
+#pragma unroll 1
+    for (int which = 0; which < 2; which++) {
+        jac o = comb_mul_tab(which == 0 ? r : sk, area, zg, hxs, hys);
+        if (which == 0) ws_store_jac(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i, o);
+        else ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, o);
+    }
+}
+
 // affine point read back from two workspace slots: (0, 0) is how the identity was stored (no curve point has y = 0)
 PLUME_DEV aff ws_load_aff_xy(uint32_t* ws, uint32_t n, int sx, int sy, uint32_t i) {
     aff p;
