@@ -170,6 +170,27 @@ int plume_ark_verify_batch_device(plume_ctx* ctx, int version, size_t n,
                                   const uint8_t* pk, const uint8_t* nullifier, const uint8_t* digest_private, const uint8_t* s,
                                   const uint8_t* r_point, const uint8_t* hashed_to_curve_r, uint8_t* ok, void* stream);
 
+/*
+ * Circuit-input side.  The circom circuit takes, next to c, s, pk and the nullifier, per-u witness hints
+ * for its hash_to_curve component (circuits/circom/verify_nullifier.circom:21-31) that the reference obtains from the
+ * external generate_inputs_from_array (circuits/circom/test/v1.test.ts:5,38-40; npm package
+ * secp256k1_hash_to_curve_circom, not vendored, no fixture in the reference pins its conventions).  These two calls
+ * produce on the device everything those inputs are made from:
+ *   plume_hash_to_curve_witness_batch   for each preimage: u0, u1 = hash_to_field (u: n x 2 x 32, big-endian canonical);
+ *                                       gx1_square[2i+k] = 1 when the SSWU map of u_k took x1 (g(x1) is a square), 0 when x2;
+ *                                       Q0, Q1 = iso_map(map_to_curve(u_k)), the circuit's x_mapped / y_mapped
+ *                                       (q: n x 2 x 64); h = Q0 + Q1 (n x 64) = plume_hash_to_curve_batch's output.
+ *   plume_registers_batch               n 32-byte big-endian values -> n x 4 little-endian 64-bit registers, least
+ *                                       significant first: scalarToCircuitValue / pointToCircuitValue of
+ *                                       circuits/circom/utils.ts:11-17,32-51 (a point is its x then its y).
+ * The square-root hints themselves (gx1_sqrt, gx2_sqrt, y_pos) depend on the generator's choice of root and are left to
+ * the caller: with u_k, the flag and Q_k they are one modular square root on the host.
+ */
+int plume_hash_to_curve_witness_batch(plume_ctx* ctx, size_t n,
+                                      const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                                      uint8_t* u, uint8_t* q, uint8_t* gx1_square, uint8_t* h);
+int plume_registers_batch(plume_ctx* ctx, size_t n, const uint8_t* in32, uint64_t* out4);
+
 /* Device-pointer variants: all pointers are device memory of the context's GPU, `stream` is a
  * cudaStream_t (passed as void* to keep CUDA headers out of this file).  n must not exceed
  * plume_ctx_chunk_items().  Work is enqueued; the caller synchronises the stream. */
@@ -195,7 +216,7 @@ uint64_t plume_ctx_launch_count(const plume_ctx* ctx);
  * stage since profiling was switched on (and their number in *launches), synchronising the
  * context's streams first.  Stage names: "sign_fixed", "sign_h2c", "sign_varbase", "sign_final",
  * "verify_h2c", "verify_mul_a" (G*s - pk*c), "verify_mul_b" (h*s - nul*c), "verify_final", "h2c_map", "h2c_out", "binv",
- * "sec1_compress", "sec1_decompress" ("verify_muls": the two as one kernel, only in -DPLUME_VERIFY_FUSED builds).
+ * "sec1_compress", "sec1_decompress", "h2c_witness", "registers" ("verify_muls": the two as one kernel, only in -DPLUME_VERIFY_FUSED builds).
  * Returns a negative value for an unknown stage.  set_profiling(ctx, 1) also resets the sums. */
 int plume_ctx_set_profiling(plume_ctx* ctx, int on);
 double plume_ctx_stage_ms(plume_ctx* ctx, const char* stage, uint64_t* launches);

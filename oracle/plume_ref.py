@@ -300,6 +300,25 @@ def ark_verify_non_zk(version, msg, pk, nul, digest_private, s, r_point, hashed_
     return ci == digest_private                                                      # :74
 
 
+def h2c_witness(msg, dst=DST):
+    """The intermediates of hash_to_curve a circuit-input generator needs: u0, u1; per u whether
+    g(x1) is a square (RFC 9380 6.6.2 step 5: x = x1 if so, else x2); Q_k = iso_map(map_to_curve(u_k)); h = Q0 + Q1."""
+    us = hash_to_field2(msg, dst)
+    flags, qs = [], []
+    for u in us:
+        tv1 = (Z * Z * pow(u, 4, P) + Z * u * u) % P
+        x1 = ISO_B * inv(Z * ISO_A) % P if tv1 == 0 else (-ISO_B) * inv(ISO_A) % P * (1 + inv(tv1)) % P
+        flags.append(1 if is_square((pow(x1, 3, P) + ISO_A * x1 + ISO_B) % P) else 0)
+        qs.append(iso_map(map_to_curve_sswu(u)))
+    return us, flags, qs, pt_add(qs[0], qs[1])
+
+
+def registers(value, bits=64, count=4):
+    """circuits/circom/utils.ts:32-51 bigIntToRegisters."""
+    assert value < (1 << (bits * count))
+    return [(value >> (bits * i)) & ((1 << bits) - 1) for i in range(count)]
+
+
 def compress33(p):
     """33-byte SEC1 slot: 02/03 || x, identity = 00 followed by zeros."""
     return bytes(33) if p is INF else encode_pt(p)

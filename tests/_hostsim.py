@@ -106,3 +106,20 @@ def h2c_batch(msgs, binv_threads=3):
     out = np.zeros((n, 64), dtype=np.uint8)
     lib().hs_h2c_batch(n, _p(blob), _p(offs), 0, _p(out), binv_threads)
     return out
+
+
+def h2c_witness_batch(msgs, binv_threads=3):
+    n = len(msgs)
+    blob, offs = _msgs(msgs)
+    o = {"u": np.zeros((n, 2, 32), dtype=np.uint8), "q": np.zeros((n, 2, 64), dtype=np.uint8),
+         "gx1_square": np.zeros((n, 2), dtype=np.uint8), "h": np.zeros((n, 64), dtype=np.uint8)}
+    lib().hs_h2c_witness_batch(n, _p(blob), _p(offs), 0, _p(o["u"]), _p(o["q"]), _p(o["gx1_square"]), _p(o["h"]), binv_threads)
+    return o
+
+
+def registers(values32):
+    a = np.ascontiguousarray(values32, dtype=np.uint8)
+    n = a.size // 32
+    out = np.zeros((n, 4), dtype=np.uint64)
+    lib().hs_registers(n, _p(a), _p(out))
+    return out

@@ -179,6 +179,23 @@ int hs_h2c_batch(uint32_t n, const uint8_t* msgs, const uint64_t* offs, uint32_t
     return 0;
 }
 
+int hs_h2c_witness_batch(uint32_t n, const uint8_t* msgs, const uint64_t* offs, uint32_t msg_len, uint8_t* u, uint8_t* q,
+                         uint8_t* gx1_square, uint8_t* h, uint32_t binv_threads) {
+    std::vector<uint32_t> ws((size_t)WS_SLOTS * n * 8);
+    h2cw_args a{};
+    a.n = n; a.msgs.base = msgs; a.msgs.offs = offs; a.msgs.fixed_len = msg_len; a.u = u; a.q = q; a.gx1_square = gx1_square; a.h = h;
+    a.ws = ws.data();
+    for (uint32_t i = 0; i < n; i++) h2cw_stage_map(i, a);
+    run_binv(a.ws, n, 2 * n, binv_threads);
+    for (uint32_t i = 0; i < n; i++) h2cw_stage_sum(i, a);
+    run_binv(a.ws, n, n, binv_threads);
+    for (uint32_t i = 0; i < n; i++) h2cw_stage_out(i, a);
+    return 0;
+}
+void hs_registers(uint32_t n, const uint8_t* in32, uint64_t* out4) {
+    for (uint32_t i = 0; i < n; i++) registers_body(i, in32, out4);
+}
+
 void hs_sec1_roundtrip(uint32_t n, const uint8_t* in33, uint8_t* out64, uint8_t* ok, uint8_t* back33) {
     for (uint32_t i = 0; i < n; i++) sec1_decompress_body(i, in33, out64, ok);
     for (uint32_t i = 0; i < n; i++) sec1_compress_body(i, out64, back33);

@@ -16,10 +16,10 @@ namespace {
 
 const char* const kStageNames[] = {"sign_fixed", "sign_h2c", "sign_varbase", "sign_final", "verify_h2c",
                                    "verify_muls", "verify_final", "h2c_map", "h2c_out", "binv", "sec1_compress", "sec1_decompress",
-                                   "verify_mul_a", "verify_mul_b"};
+                                   "verify_mul_a", "verify_mul_b", "h2c_witness", "registers"};
 enum Stage { ST_SIGN_FIXED, ST_SIGN_H2C, ST_SIGN_VARBASE, ST_SIGN_FINAL, ST_VERIFY_H2C, ST_VERIFY_MULS,
              ST_VERIFY_FINAL, ST_H2C_MAP, ST_H2C_OUT, ST_BINV, ST_SEC1_COMPRESS, ST_SEC1_DECOMPRESS, ST_VERIFY_MUL_A,
-             ST_VERIFY_MUL_B, ST_COUNT };
+             ST_VERIFY_MUL_B, ST_H2C_WITNESS, ST_REGISTERS, ST_COUNT };
 
 struct PendingCopy { void* dst; const void* src; size_t bytes; };
 
@@ -138,6 +138,15 @@ int enqueue_h2c(plume_ctx* ctx, h2c_args a, cudaStream_t s) {
     RUN(ST_H2C_MAP, launch_h2c_map(a, s));
     if (int rc = binv(ctx, a.ws, a.n, a.n, s)) return rc;
     RUN(ST_H2C_OUT, launch_h2c_out(a, s));
+    return PLUME_OK;
+}
+
+int enqueue_h2cw(plume_ctx* ctx, h2cw_args a, cudaStream_t s) {
+    RUN(ST_H2C_WITNESS, launch_h2cw(0, a, s));
+    if (int rc = binv(ctx, a.ws, a.n, 2 * a.n, s)) return rc;
+    RUN(ST_H2C_WITNESS, launch_h2cw(1, a, s));
+    if (int rc = binv(ctx, a.ws, a.n, a.n, s)) return rc;
+    RUN(ST_H2C_WITNESS, launch_h2cw(2, a, s));
     return PLUME_OK;
 }
 
@@ -639,6 +648,65 @@ int plume_hash_to_curve_batch(plume_ctx* ctx, size_t n, const uint8_t* msgs, con
         a.ws = L.ws;
         if (int rc = enqueue_h2c(ctx, a, L.stream)) return rc;
         if (int rc = lane_fetch(ctx, L, out + i0 * 64, o_out, cn * 64)) return rc;
+    }
+    for (Lane& L : ctx->lanes) if (int rc = lane_finish(ctx, L)) return rc;
+    return PLUME_OK;
+}
+
+int plume_hash_to_curve_witness_batch(plume_ctx* ctx, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                                      uint8_t* u, uint8_t* q, uint8_t* gx1_square, uint8_t* h) {
+    if (int rc = check_common(ctx, n, msgs, msg_offsets, msg_len)) return rc;
+    if (n == 0) return PLUME_OK;
+    if (!u || !q || !gx1_square || !h) return fail(ctx, PLUME_E_ARG, "null array");
+    ScopedDevice sd(ctx->device);
+    size_t k = 0;
+    for (size_t i0 = 0; i0 < n; i0 += ctx->host_chunk, k++) {
+        const size_t cn = (n - i0 < ctx->host_chunk) ? n - i0 : ctx->host_chunk;
+        Lane& L = ctx->lanes[k & 1];
+        if (int rc = lane_finish(ctx, L)) return rc;
+        if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * (64 + 128 + 2 + 64) + 4096)) return rc;
+        L.d_io_used = 0;
+        L.busy = true;
+        h2cw_args a{};
+        a.n = (uint32_t)cn;
+        if (int rc = lane_msgs(ctx, L, msgs, msg_offsets, msg_len, i0, cn, &a.msgs)) return rc;
+        size_t o_u, o_q, o_f, o_h;
+        a.u = lane_output(L, cn * 64, &o_u);
+        a.q = lane_output(L, cn * 128, &o_q);
+        a.gx1_square = lane_output(L, cn * 2, &o_f);
+        a.h = lane_output(L, cn * 64, &o_h);
+        a.ws = L.ws;
+        if (int rc = enqueue_h2cw(ctx, a, L.stream)) return rc;
+        if (int rc = lane_fetch(ctx, L, u + i0 * 64, o_u, cn * 64)) return rc;
+        if (int rc = lane_fetch(ctx, L, q + i0 * 128, o_q, cn * 128)) return rc;
+        if (int rc = lane_fetch(ctx, L, gx1_square + i0 * 2, o_f, cn * 2)) return rc;
+        if (int rc = lane_fetch(ctx, L, h + i0 * 64, o_h, cn * 64)) return rc;
+    }
+    for (Lane& L : ctx->lanes) if (int rc = lane_finish(ctx, L)) return rc;
+    return PLUME_OK;
+}
+
+int plume_registers_batch(plume_ctx* ctx, size_t n, const uint8_t* in32, uint64_t* out4) {
+    if (!ctx) return PLUME_E_ARG;
+    if (n == 0) return PLUME_OK;
+    if (!in32 || !out4) return fail(ctx, PLUME_E_ARG, "null array");
+    ScopedDevice sd(ctx->device);
+    size_t k = 0;
+    const size_t step = ctx->host_chunk * 4;
+    for (size_t i0 = 0; i0 < n; i0 += step, k++) {
+        const size_t cn = (n - i0 < step) ? n - i0 : step;
+        Lane& L = ctx->lanes[k & 1];
+        if (int rc = lane_finish(ctx, L)) return rc;
+        if (int rc = lane_reserve(ctx, L, cn * 64 + 4096)) return rc;
+        L.d_io_used = 0;
+        L.busy = true;
+        uint8_t* d_in;
+        if (int rc = lane_input(ctx, L, in32 + i0 * 32, cn * 32, &d_in)) return rc;
+        size_t o_out;
+        uint8_t* d_out = lane_output(L, cn * 32, &o_out);
+        cudaStream_t s = L.stream;
+        RUN(ST_REGISTERS, launch_registers((uint32_t)cn, d_in, reinterpret_cast<uint64_t*>(d_out), s));
+        if (int rc = lane_fetch(ctx, L, reinterpret_cast<uint8_t*>(out4) + i0 * 32, o_out, cn * 32)) return rc;
     }
     for (Lane& L : ctx->lanes) if (int rc = lane_finish(ctx, L)) return rc;
     return PLUME_OK;

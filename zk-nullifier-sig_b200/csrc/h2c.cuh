@@ -117,7 +117,7 @@ PLUME_DEV bool h2c_sqrt_ratio(fe& y, const fe& u, const fe& v) {
 }
 
 // simplified SWU on E': y^2 = x^3 + A'x + B' (RFC 9380 F.2, straight line); x = xn / xd
-PLUME_DEV void h2c_map_sswu(fe& xn, fe& xd, fe& y, const fe& u) {
+PLUME_DEV bool h2c_map_sswu(fe& xn, fe& xd, fe& y, const fe& u) {   // returns is_square(g(x1)): which candidate x was taken
     const fe A = h2c_iso_a();
     fe tv1 = fe_neg(fe_mul_small(fe_sqr(u), 11));  // Z * u^2, Z = -11
     fe tv2 = fe_add(fe_sqr(tv1), tv1);
@@ -142,6 +142,7 @@ PLUME_DEV void h2c_map_sswu(fe& xn, fe& xd, fe& y, const fe& u) {
     y = fe_cmov(fe_neg(yy), yy, e1);
     xn = x;
     xd = tv4;
+    return is_gx1_square;
 }
 
 // 3-isogeny E' -> secp256k1 on x' = xn/xd (RFC 9380 E.1), result in Jacobian coordinates

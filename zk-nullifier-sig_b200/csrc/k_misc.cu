@@ -5,6 +5,22 @@ __global__ void __launch_bounds__(128, PLUME_H2C_MINBLOCKS) k_h2c_map(h2c_args a
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.n) h2c_stage_map(i, a);
 }
+__global__ void __launch_bounds__(128, PLUME_H2C_MINBLOCKS) k_h2cw_map(h2cw_args a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) h2cw_stage_map(i, a);
+}
+__global__ void __launch_bounds__(128) k_h2cw_sum(h2cw_args a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) h2cw_stage_sum(i, a);
+}
+__global__ void __launch_bounds__(128) k_h2cw_out(h2cw_args a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) h2cw_stage_out(i, a);
+}
+__global__ void __launch_bounds__(256) k_registers(uint32_t n, const uint8_t* in32, uint64_t* out4) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) registers_body(i, in32, out4);
+}
 __global__ void __launch_bounds__(128) k_h2c_out(h2c_args a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.n) h2c_stage_out(i, a);
@@ -123,6 +139,16 @@ static inline unsigned grid_for(uint32_t n, unsigned b) { return (n + b - 1) / b
 
 cudaError_t launch_h2c_map(const h2c_args& a, cudaStream_t s) {
     k_h2c_map<<<grid_for(a.n, 128), 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_h2cw(int stage, const h2cw_args& a, cudaStream_t s) {
+    if (stage == 0) k_h2cw_map<<<grid_for(a.n, 128), 128, 0, s>>>(a);
+    else if (stage == 1) k_h2cw_sum<<<grid_for(a.n, 128), 128, 0, s>>>(a);
+    else k_h2cw_out<<<grid_for(a.n, 128), 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_registers(uint32_t n, const uint8_t* in32, uint64_t* out4, cudaStream_t s) {
+    k_registers<<<grid_for(n, 256), 256, 0, s>>>(n, in32, out4);
     return cudaGetLastError();
 }
 cudaError_t launch_h2c_out(const h2c_args& a, cudaStream_t s) {

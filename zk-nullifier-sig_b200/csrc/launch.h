@@ -50,6 +50,8 @@ cudaError_t launch_verify_mul_a(const verify_args& a, cudaStream_t s);   // G*s 
 cudaError_t launch_verify_final(const verify_args& a, cudaStream_t s);
 cudaError_t launch_h2c_map(const h2c_args& a, cudaStream_t s);
 cudaError_t launch_h2c_out(const h2c_args& a, cudaStream_t s);
+cudaError_t launch_h2cw(int stage, const h2cw_args& a, cudaStream_t s);   // 0 map, 1 sum, 2 out
+cudaError_t launch_registers(uint32_t n, const uint8_t* in32, uint64_t* out4, cudaStream_t s);
 // batched inversion of m elements at Z (scratch same size), `per_thread` elements per thread
 cudaError_t launch_binv(uint32_t* Z, uint32_t* scratch, uint32_t m, uint32_t per_thread, cudaStream_t s);
 // generator table

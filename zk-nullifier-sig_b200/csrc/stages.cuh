@@ -590,6 +590,62 @@ PLUME_DEV void h2c_stage_out(uint32_t i, const h2c_args& a) {
     st_point_be(a.out + (size_t)i * 64, h);
 }
 
+// ---- hash_to_curve with its intermediates (what a circuit-input generator starts from) ----------------
+// The verify_nullifier circuit takes per-u witness hints (circuits/circom/verify_nullifier.circom:21-31) produced today by
+// the external generate_inputs_from_array (circuits/circom/test/v1.test.ts:5,38-40).  The device computes the RFC 9380
+// values those hints are derived from: u0, u1 = hash_to_field, which SSWU candidate was taken (g(x1) square or not),
+// the mapped points Q0, Q1 = iso_map(map_to_curve(u_k)) ("x_mapped", "y_mapped") and h = Q0 + Q1.
+struct h2cw_args {
+    uint32_t n;
+    msg_view msgs;
+    uint8_t* u;          // n x 2 x 32  big-endian canonical u0, u1
+    uint8_t* q;          // n x 2 x 64  Q0, Q1 affine
+    uint8_t* gx1_square; // n x 2       1 when g(x1) is a square (x = x1), 0 when x = x2 = Z u^2 x1
+    uint8_t* h;          // n x 64      Q0 + Q1
+    uint32_t* ws;
+};
+PLUME_DEV void h2cw_stage_map(uint32_t i, const h2cw_args& a) {
+    uint32_t len;
+    const uint8_t* m = msg_ptr(a.msgs, i, len);
+    fe u0, u1;
+    h2c_hash_to_field(u0, u1, m, len, m, 0);
+#pragma unroll 1
+    for (int k = 0; k < 2; k++) {
+        fe u = fe_norm(k == 0 ? u0 : u1);
+        st_fe_be(a.u + ((size_t)i * 2 + k) * 32, u);
+        fe xn, xd, y;
+        bool sq = h2c_map_sswu(xn, xd, y, u);
+        a.gx1_square[(size_t)i * 2 + k] = sq ? 1 : 0;
+        jac qk = h2c_iso_map(xn, xd, y);
+        if (k == 0) ws_store_jac(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i, qk);
+        else ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, qk);
+    }
+}
+PLUME_DEV void h2cw_stage_sum(uint32_t i, const h2cw_args& a) {
+    aff q0 = ws_load_affine(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i);
+    aff q1 = ws_load_affine(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i);
+    st_point_be(a.q + (size_t)i * 128, q0);
+    st_point_be(a.q + (size_t)i * 128 + 64, q1);
+    jac h = jac_add_aff(jac_from_aff(q0), q1.x, q1.y, q1.inf);
+    ws_store_jac(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i, h);
+}
+PLUME_DEV void h2cw_stage_out(uint32_t i, const h2cw_args& a) {
+    aff h = ws_load_affine(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i);
+    st_point_be(a.h + (size_t)i * 64, h);
+}
+// 32 big-endian bytes -> the circuit's four 64-bit registers, least significant first (circuits/circom/utils.ts:11-17,32-51:
+// bigIntToRegisters(value, 64, 4)); as bytes that is the reversal of the 32-byte string
+PLUME_DEV void registers_body(uint32_t i, const uint8_t* in32, uint64_t* out4) {
+    const uint8_t* s = in32 + (size_t)i * 32;
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+        uint64_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 8; b++) v = (v << 8) | s[(3 - r) * 8 + b];
+        out4[(size_t)i * 4 + r] = v;
+    }
+}
+
 // ---- SEC1-compressed wire form (the form the JS binding exchanges, javascript/src/lib.rs:97-117) ----
 // 33-byte slots: 02/03 || x for a finite point, 00 followed by 32 zero bytes for the identity.
 PLUME_DEV void sec1_compress_body(uint32_t i, const uint8_t* in64, uint8_t* out33) {

@@ -20,6 +20,9 @@ SYMBOLS = {
     "plume_verify_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, _u8p, _u8p, ctypes.c_size_t,
                                           _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p]),
     "plume_hash_to_curve_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, _u8p, _u8p, ctypes.c_size_t, _u8p]),
+    "plume_hash_to_curve_witness_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, _u8p, _u8p, ctypes.c_size_t,
+                                                         _u8p, _u8p, _u8p, _u8p]),
+    "plume_registers_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, _u8p, _u8p]),
     "plume_ark_sign_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, _u8p, _u8p, ctypes.c_size_t,
                                             _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p]),
     "plume_ark_verify_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, _u8p, _u8p, ctypes.c_size_t,

@@ -164,6 +164,25 @@ class PlumeContext:
         self._check(rc, "plume_verify_batch")
         return ok
 
+    # ---- circuit-input side ----------------------------------------------------------------
+    def hash_to_curve_witness_batch(self, msgs):
+        """plume_hash_to_curve_witness_batch: dict u [n,2,32], q [n,2,64], gx1_square [n,2], h [n,64]."""
+        blob, offs, mlen, n = self._msgs(msgs, None)
+        o = {"u": np.empty((n, 2, 32), dtype=np.uint8), "q": np.empty((n, 2, 64), dtype=np.uint8),
+             "gx1_square": np.empty((n, 2), dtype=np.uint8), "h": np.empty((n, 64), dtype=np.uint8)}
+        rc = self._lib.plume_hash_to_curve_witness_batch(self._h, n, _ptr(blob), _ptr(offs), mlen, _ptr(o["u"]), _ptr(o["q"]),
+                                                         _ptr(o["gx1_square"]), _ptr(o["h"]))
+        self._check(rc, "plume_hash_to_curve_witness_batch")
+        return o
+
+    def registers_batch(self, values32):
+        """plume_registers_batch: u8[..., 32] big-endian -> u64[..., 4] (circuits/circom/utils.ts scalarToCircuitValue)."""
+        a = _as_u8(values32)
+        n = a.size // 32
+        out = np.empty((n, 4), dtype=np.uint64)
+        self._check(self._lib.plume_registers_batch(self._h, n, _ptr(a), _ptr(out)), "plume_registers_batch")
+        return out.reshape(a.shape[:-1] + (4,)) if a.ndim > 1 else out
+
     # ---- arkworks flavour (rust-arkworks/src/lib.rs:229-278, tests.rs:28-78) -----------------------------
     def ark_sign_batch(self, version, msgs, pk, sk, r):
         """plume_ark_sign_batch.  pk: u8[n,64] (input); sk, r: u8[n,32] big-endian Fr (zero allowed)."""
