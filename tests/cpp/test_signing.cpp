@@ -48,5 +48,15 @@ int main(int argc, char** argv) {
     size_t good = 0;
     for (size_t i = 0; i < n; i++) good += (out.status[i] == 0 && ok[i] == 1);
     printf("batch %zu\n", good);
+    // the arkworks twin on the same vector (rust-arkworks/src/tests.rs:267-300): pk is an input here
+    for (auto ver : {plume::ark::PlumeVersion::V1, plume::ark::PlumeVersion::V2}) {
+        auto sig = plume::ark::sign_with_r(s1.pk, sk.to_bytes(), msg, unhex(argv[3]), ver);
+        bool good_sig = plume::ark::verify_non_zk(sig.first, sig.second, s1.pk, msg, ver);
+        auto bad = sig.first; bad.s[31] ^= 1;
+        printf("ark v%d %s %s %d %d\n", (int)ver, hex(sig.second.digest_private).c_str(), hex(sig.first.s).c_str(), (int)good_sig,
+               (int)plume::ark::verify_non_zk(bad, sig.second, s1.pk, msg, ver));
+    }
+    try { plume::ark::sign_with_r(plume::AffinePoint{}, sk.to_bytes(), msg, unhex(argv[3]), plume::ark::PlumeVersion::V2); printf("identity-pk accepted\n"); }
+    catch (const plume::ark::HashToCurveError&) { printf("identity-pk rejected\n"); }
     return 0;
 }

@@ -257,6 +257,9 @@ def test_cpp_host_mirror(golden, tmp_path):
     assert out[0] == "v1 %s %s 1 1" % (k["v1_c"]["hex"], k["v1_s"]["hex"])
     assert out[1] == "v2 %s %s 1 0" % (k["v2_c"]["hex"], k["v2_s"]["hex"])
     assert out[2] == "tampered 0" and out[3] == "zero-sk rejected" and out[4] == "batch 1000"
+    assert out[5] == "ark v1 %s %s 1 0" % (k["v1_c"]["hex"], k["v1_s"]["hex"])      # rust-arkworks/src/tests.rs:281-299
+    assert out[6] == "ark v2 %s %s 1 0" % (k["v2_c"]["hex"], k["v2_s"]["hex"])
+    assert out[7] == "identity-pk rejected"
 
 
 def test_sec1_compressed_api(gpu_ctx):

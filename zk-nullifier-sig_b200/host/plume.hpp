@@ -20,6 +20,7 @@
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "plume_b200.h"
@@ -187,5 +188,53 @@ inline std::vector<uint8_t> verify_batch(Context& cx, int version, size_t n, con
              "plume_verify_batch");
     return ok;
 }
+
+// ---- the arkworks twin (rust-arkworks/src/lib.rs), SURVEY.md 8f-3 -----------------------------------------------
+namespace ark {
+enum class PlumeVersion { V1 = 1, V2 = 2 };                       // lib.rs:65-69
+using Fr = Bytes32;                                                // big-endian, in [0, n)
+struct HashToCurveError : Error { using Error::Error; };           // hash_to_curve on the identity pk (lib.rs:97-100)
+struct PlumeSignaturePublic {                                      // lib.rs:175-183
+    std::vector<uint8_t> message;
+    Fr s{};
+    AffinePoint nullifier;
+    std::optional<PlumeVersion> variant;
+};
+struct PlumeSignaturePrivate {                                     // lib.rs:185-194
+    AffinePoint hashed_to_curve_r, r_point;
+    Fr digest_private{};
+    PlumeVersion variant{PlumeVersion::V1};
+};
+// lib.rs:229-278: keypair = (pk, sk); nothing is rejected but an identity / off-curve pk and scalars >= n
+inline std::pair<PlumeSignaturePublic, PlumeSignaturePrivate> sign_with_r(const AffinePoint& pk, const Fr& sk, const std::vector<uint8_t>& message,
+                                                                          const Fr& r_scalar, PlumeVersion version,
+                                                                          std::shared_ptr<Context> cx = nullptr) {
+    if (!cx) cx = Context::global();
+    PlumeSignaturePublic pub;
+    PlumeSignaturePrivate priv;
+    uint8_t st = 0;
+    cx->check(plume_ark_sign_batch(cx->get(), (int)version, 1, message.data(), nullptr, message.size(), pk.xy.data(), sk.data(), r_scalar.data(),
+                                   pub.nullifier.xy.data(), priv.digest_private.data(), pub.s.data(), priv.r_point.xy.data(),
+                                   priv.hashed_to_curve_r.xy.data(), &st),
+              "plume_ark_sign_batch");
+    if (st == PLUME_STATUS_BAD_PK) throw HashToCurveError("`pk` shouldn't be the identity element");
+    if (st != PLUME_STATUS_OK) throw Error("scalar is not a canonical Fr");
+    pub.message = message;
+    pub.variant = version;
+    priv.variant = version;
+    return {pub, priv};
+}
+// rust-arkworks/src/tests.rs:28-78
+inline bool verify_non_zk(const PlumeSignaturePublic& pub, const PlumeSignaturePrivate& priv, const AffinePoint& pk,
+                          const std::vector<uint8_t>& message, PlumeVersion version, std::shared_ptr<Context> cx = nullptr) {
+    if (!cx) cx = Context::global();
+    if (pk.is_identity()) throw HashToCurveError("`pk` shouldn't be the identity element");
+    uint8_t ok = 0;
+    cx->check(plume_ark_verify_batch(cx->get(), (int)version, 1, message.data(), nullptr, message.size(), pk.xy.data(), pub.nullifier.xy.data(),
+                                     priv.digest_private.data(), pub.s.data(), priv.r_point.xy.data(), priv.hashed_to_curve_r.xy.data(), &ok),
+              "plume_ark_verify_batch");
+    return ok != 0;
+}
+}  // namespace ark
 
 }  // namespace plume

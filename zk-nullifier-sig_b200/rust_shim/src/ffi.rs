@@ -39,4 +39,22 @@ extern "C" {
         sk: *const u8, r: *const u8, pk: *mut u8, nullifier: *mut u8, c: *mut u8, s: *mut u8,
         r_point: *mut u8, hashed_to_curve_r: *mut u8, status: *mut u8, stream: *mut c_void,
     ) -> c_int;
+    // SEC1-compressed forms, the arkworks flavour and the circuit-input side (include/plume_b200.h); UNTESTED like the rest
+    pub fn plume_points_compress_batch(ctx: *mut plume_ctx, n: usize, in64: *const u8, out33: *mut u8) -> c_int;
+    pub fn plume_points_decompress_batch(ctx: *mut plume_ctx, n: usize, in33: *const u8, out64: *mut u8, ok: *mut u8) -> c_int;
+    pub fn plume_ark_sign_batch(
+        ctx: *mut plume_ctx, version: c_int, n: usize, msgs: *const u8, msg_offsets: *const u64, msg_len: usize,
+        pk: *const u8, sk: *const u8, r: *const u8, nullifier: *mut u8, digest_private: *mut u8, s: *mut u8,
+        r_point: *mut u8, hashed_to_curve_r: *mut u8, status: *mut u8,
+    ) -> c_int;
+    pub fn plume_ark_verify_batch(
+        ctx: *mut plume_ctx, version: c_int, n: usize, msgs: *const u8, msg_offsets: *const u64, msg_len: usize,
+        pk: *const u8, nullifier: *const u8, digest_private: *const u8, s: *const u8,
+        r_point: *const u8, hashed_to_curve_r: *const u8, ok: *mut u8,
+    ) -> c_int;
+    pub fn plume_hash_to_curve_witness_batch(
+        ctx: *mut plume_ctx, n: usize, msgs: *const u8, msg_offsets: *const u64, msg_len: usize,
+        u: *mut u8, q: *mut u8, gx1_square: *mut u8, h: *mut u8,
+    ) -> c_int;
+    pub fn plume_registers_batch(ctx: *mut plume_ctx, n: usize, in32: *const u8, out4: *mut u64) -> c_int;
 }
