@@ -242,6 +242,14 @@ size_t msgs_bytes(const uint64_t* offs, size_t msg_len, size_t i0, size_t cn) {
     return offs ? (size_t)(offs[i0 + cn] - offs[i0]) + (cn + 1) * 8 + 512 : cn * msg_len + 256;
 }
 
+// Length of the chunk of a host-pointer call that starts at item i0.  The first chunk is a third of the others (one wave
+// of the 4-blocks-per-SM kernels): its upload is the part of the call no computation can hide, so it is kept short.
+size_t host_chunk_len(const plume_ctx* ctx, size_t n, size_t i0) {
+    size_t want = ctx->host_chunk;
+    if (i0 == 0 && n > ctx->host_chunk && ctx->host_chunk >= 3 * 128) want = ctx->host_chunk / 3;
+    return (n - i0 < want) ? n - i0 : want;
+}
+
 int check_common(plume_ctx* ctx, size_t n, const uint8_t* msgs, const uint64_t* offs, size_t msg_len) {
     if (!ctx) return PLUME_E_ARG;
     if (n > 0 && !msgs && (offs ? offs[n] != offs[0] : msg_len != 0)) return fail(ctx, PLUME_E_ARG, "msgs is null");
@@ -520,8 +528,8 @@ int sign_host(plume_ctx* ctx, int flavour, int version, size_t n, const uint8_t*
     if (flavour == PLUME_FLAVOUR_ARKWORKS ? !pk_in : !pk) return fail(ctx, PLUME_E_ARG, "null pk array");
     ScopedDevice sd(ctx->device);
     size_t k = 0;
-    for (size_t i0 = 0; i0 < n; i0 += ctx->host_chunk, k++) {
-        const size_t cn = (n - i0 < ctx->host_chunk) ? n - i0 : ctx->host_chunk;
+    for (size_t i0 = 0, cn = 0; i0 < n; i0 += cn, k++) {
+        cn = host_chunk_len(ctx, n, i0);
         Lane& L = ctx->lanes[k & 1];
         if (int rc = lane_finish(ctx, L)) return rc;
         if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * (64 + 64 * 4 + 64 + 1) + 4096)) return rc;
@@ -568,8 +576,8 @@ int verify_host(plume_ctx* ctx, int flavour, int version, size_t n, const uint8_
     if (need_points && (!r_point || !hashed_to_curve_r)) return fail(ctx, PLUME_E_ARG, "r_point and hashed_to_curve_r are required");
     ScopedDevice sd(ctx->device);
     size_t k = 0;
-    for (size_t i0 = 0; i0 < n; i0 += ctx->host_chunk, k++) {
-        const size_t cn = (n - i0 < ctx->host_chunk) ? n - i0 : ctx->host_chunk;
+    for (size_t i0 = 0, cn = 0; i0 < n; i0 += cn, k++) {
+        cn = host_chunk_len(ctx, n, i0);
         Lane& L = ctx->lanes[k & 1];
         if (int rc = lane_finish(ctx, L)) return rc;
         if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * (64 * 4 + 64 + 1) + 4096)) return rc;
@@ -633,8 +641,8 @@ int plume_hash_to_curve_batch(plume_ctx* ctx, size_t n, const uint8_t* msgs, con
     if (!out) return fail(ctx, PLUME_E_ARG, "null array");
     ScopedDevice sd(ctx->device);
     size_t k = 0;
-    for (size_t i0 = 0; i0 < n; i0 += ctx->host_chunk, k++) {
-        const size_t cn = (n - i0 < ctx->host_chunk) ? n - i0 : ctx->host_chunk;
+    for (size_t i0 = 0, cn = 0; i0 < n; i0 += cn, k++) {
+        cn = host_chunk_len(ctx, n, i0);
         Lane& L = ctx->lanes[k & 1];
         if (int rc = lane_finish(ctx, L)) return rc;
         if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * 64 + 4096)) return rc;
@@ -660,8 +668,8 @@ int plume_hash_to_curve_witness_batch(plume_ctx* ctx, size_t n, const uint8_t* m
     if (!u || !q || !gx1_square || !h) return fail(ctx, PLUME_E_ARG, "null array");
     ScopedDevice sd(ctx->device);
     size_t k = 0;
-    for (size_t i0 = 0; i0 < n; i0 += ctx->host_chunk, k++) {
-        const size_t cn = (n - i0 < ctx->host_chunk) ? n - i0 : ctx->host_chunk;
+    for (size_t i0 = 0, cn = 0; i0 < n; i0 += cn, k++) {
+        cn = host_chunk_len(ctx, n, i0);
         Lane& L = ctx->lanes[k & 1];
         if (int rc = lane_finish(ctx, L)) return rc;
         if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * (64 + 128 + 2 + 64) + 4096)) return rc;
@@ -736,8 +744,8 @@ int plume_points_compress_batch(plume_ctx* ctx, size_t n, const uint8_t* in64, u
     if (!in64 || !out33) return fail(ctx, PLUME_E_ARG, "null array");
     ScopedDevice sd(ctx->device);
     size_t k = 0;
-    for (size_t i0 = 0; i0 < n; i0 += ctx->host_chunk, k++) {
-        const size_t cn = (n - i0 < ctx->host_chunk) ? n - i0 : ctx->host_chunk;
+    for (size_t i0 = 0, cn = 0; i0 < n; i0 += cn, k++) {
+        cn = host_chunk_len(ctx, n, i0);
         Lane& L = ctx->lanes[k & 1];
         if (int rc = lane_finish(ctx, L)) return rc;
         if (int rc = lane_reserve(ctx, L, cn * 97 + 4096)) return rc;
@@ -761,8 +769,8 @@ int plume_points_decompress_batch(plume_ctx* ctx, size_t n, const uint8_t* in33,
     if (!in33 || !out64 || !ok) return fail(ctx, PLUME_E_ARG, "null array");
     ScopedDevice sd(ctx->device);
     size_t k = 0;
-    for (size_t i0 = 0; i0 < n; i0 += ctx->host_chunk, k++) {
-        const size_t cn = (n - i0 < ctx->host_chunk) ? n - i0 : ctx->host_chunk;
+    for (size_t i0 = 0, cn = 0; i0 < n; i0 += cn, k++) {
+        cn = host_chunk_len(ctx, n, i0);
         Lane& L = ctx->lanes[k & 1];
         if (int rc = lane_finish(ctx, L)) return rc;
         if (int rc = lane_reserve(ctx, L, cn * 98 + 4096)) return rc;
@@ -791,8 +799,8 @@ int plume_sign_batch_sec1(plume_ctx* ctx, int version, size_t n, const uint8_t* 
     if (!sk || !r || !pk33 || !nullifier33 || !c || !s_out || !status) return fail(ctx, PLUME_E_ARG, "null array");
     ScopedDevice sd(ctx->device);
     size_t k = 0;
-    for (size_t i0 = 0; i0 < n; i0 += ctx->host_chunk, k++) {
-        const size_t cn = (n - i0 < ctx->host_chunk) ? n - i0 : ctx->host_chunk;
+    for (size_t i0 = 0, cn = 0; i0 < n; i0 += cn, k++) {
+        cn = host_chunk_len(ctx, n, i0);
         Lane& L = ctx->lanes[k & 1];
         if (int rc = lane_finish(ctx, L)) return rc;
         if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * (64 + 64 * 4 + 33 * 4 + 64 + 1) + 8192)) return rc;
@@ -842,8 +850,8 @@ int plume_verify_batch_sec1(plume_ctx* ctx, int version, size_t n, const uint8_t
     if (version == 1 && (!r_point33 || !hashed_to_curve_r33)) return fail(ctx, PLUME_E_ARG, "V1 needs r_point and hashed_to_curve_r");
     ScopedDevice sd(ctx->device);
     size_t k = 0;
-    for (size_t i0 = 0; i0 < n; i0 += ctx->host_chunk, k++) {
-        const size_t cn = (n - i0 < ctx->host_chunk) ? n - i0 : ctx->host_chunk;
+    for (size_t i0 = 0, cn = 0; i0 < n; i0 += cn, k++) {
+        cn = host_chunk_len(ctx, n, i0);
         Lane& L = ctx->lanes[k & 1];
         if (int rc = lane_finish(ctx, L)) return rc;
         if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * (33 * 4 + 64 * 4 + 64 + 5) + 8192)) return rc;
