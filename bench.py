@@ -52,10 +52,11 @@ WORK_MS = {                                # (M, S); M + S reproduces the totals
     "fixed_pair": (512, 192),              # g^r, g^sk: 2 x 32 mixed additions                                             = 704
     "sign_varbase": (1270, 1568),          # h^r, h^sk sharing one table: 2 x (128 dbl + 43 add) + table                    = 2838
     "verify_mul_a": (886, 880),            # G*s - pk*c: 128 dbl + 70 add + table                                           = 1766
-    "verify_mul_b": (1170, 1044),          # h*s - nul*c: 128 dbl + 86 add + two tables                                     = 2214
+    "verify_mul_b": (1030, 984),           # h*s - nul*c, the ladder: 128 dbl + 86 add                                      = 2014
+    "verify_tab_b": (140, 60),             #              its two window tables                                              = 200
     "affine_out": (300, 0),                # batched conversion of 3-5 output points
 }
-WORK_MS["verify_muls"] = tuple(a + b for a, b in zip(WORK_MS["verify_mul_a"], WORK_MS["verify_mul_b"]))
+WORK_MS["verify_muls"] = tuple(a + b + c for a, b, c in zip(WORK_MS["verify_mul_a"], WORK_MS["verify_mul_b"], WORK_MS["verify_tab_b"]))
 WORK_MS["sign"] = tuple(sum(WORK_MS[k][i] for k in ("h2c_map", "sign_varbase", "fixed_pair", "affine_out")) for i in (0, 1))   # 4478
 WORK_MS["verify"] = tuple(sum(WORK_MS[k][i] for k in ("h2c_map", "verify_muls", "affine_out")) for i in (0, 1))               # 4916
 WORK_MS["h2c"] = tuple(sum(WORK_MS[k][i] for k in ("h2c_map", "inversion")) for i in (0, 1))                                   # 906
@@ -71,7 +72,7 @@ def work_lp(kind, survey_units=False):
 
 # algorithmic bytes per item of the dominant kernels (what they must read + write in HBM)
 BYTES = {"sign_varbase": 3 * 32 + 64 + 2 * 32 + 6 * 32, "verify_muls": 3 * 32 + 64 * 2 + 64 + 2 * 32 + 6 * 32,
-         "verify_mul_a": 64 + 2 * 32 + 3 * 32, "verify_mul_b": 3 * 32 + 64 + 2 * 32 + 2 * 32 + 3 * 32}
+         "verify_mul_a": 64 + 2 * 32 + 3 * 32, "verify_mul_b": 2 * 32 + 32 + 3 * 32, "verify_tab_b": 3 * 32 + 64 + 3 * 32}
 
 
 _K256 = np.array([
@@ -405,7 +406,7 @@ def main():
     dev_ms = e0.elapsed_time(e1)
     launches = ctx.launch_count - launches0
     stage = {}
-    for st in ("sign_fixed", "sign_h2c", "sign_varbase", "sign_final", "verify_h2c", "verify_muls", "verify_mul_a", "verify_mul_b", "verify_final", "h2c_map",
+    for st in ("sign_fixed", "sign_h2c", "sign_varbase", "sign_final", "verify_h2c", "verify_muls", "verify_mul_a", "verify_tab_b", "verify_mul_b", "verify_final", "h2c_map",
                "h2c_out", "binv", "sec1_compress", "sec1_decompress"):
         ms, k = ctx.stage_ms(st)
         if k:

@@ -215,7 +215,7 @@ uint64_t plume_ctx_launch_count(const plume_ctx* ctx);
  * plume_ctx_stage_ms returns the summed duration in milliseconds of all launches of the named
  * stage since profiling was switched on (and their number in *launches), synchronising the
  * context's streams first.  Stage names: "sign_fixed", "sign_h2c", "sign_varbase", "sign_final",
- * "verify_h2c", "verify_mul_a" (G*s - pk*c), "verify_mul_b" (h*s - nul*c), "verify_final", "h2c_map", "h2c_out", "binv",
+ * "verify_h2c", "verify_mul_a" (G*s - pk*c), "verify_tab_b" + "verify_mul_b" (window tables and ladder of h*s - nul*c), "verify_final", "h2c_map", "h2c_out", "binv",
  * "sec1_compress", "sec1_decompress", "h2c_witness", "registers" ("verify_muls": the two as one kernel, only in -DPLUME_VERIFY_FUSED builds).
  * Returns a negative value for an unknown stage.  set_profiling(ctx, 1) also resets the sums. */
 int plume_ctx_set_profiling(plume_ctx* ctx, int on);

@@ -96,7 +96,7 @@ def verify_batch(version, msgs, pk, nullifier, c, s, r_point, hashed_to_curve_r,
     a = [np.ascontiguousarray(x, dtype=np.uint8) for x in (pk, nullifier, c, s, r_point, hashed_to_curve_r)]
     ok = np.zeros(n, dtype=np.uint8)
     lib().hs_verify_batch(0, version, n, _p(blob), _p(offs), 0, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), _p(a[5]), _p(ok),
-                          gw, binv_threads, 1 if fused else 0)
+                          gw, binv_threads, int(fused))
     return ok
 
 

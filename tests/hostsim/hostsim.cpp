@@ -145,7 +145,8 @@ int hs_sign_batch(int flavour, int comb, int version, uint32_t n, const uint8_t*
     return 0;
 }
 
-// fused != 0 runs the one-kernel form of the multiplication stage (-DPLUME_VERIFY_FUSED builds), else the shipped two
+// fused: 0 the shipped form (table kernel + ladder kernel + G*s - pk*c kernel), 1 everything in one kernel
+// (-DPLUME_VERIFY_FUSED), 2 tables and ladder of h*s - nul*c in one kernel (-DPLUME_VERIFY_B_ONE)
 int hs_verify_batch(int flavour, int version, uint32_t n, const uint8_t* msgs, const uint64_t* offs, uint32_t msg_len,
                     const uint8_t* pk, const uint8_t* nul, const uint8_t* c, const uint8_t* s,
                     const uint8_t* r_point, const uint8_t* hr, uint8_t* ok, int gw, uint32_t binv_threads, int fused) {
@@ -161,8 +162,17 @@ int hs_verify_batch(int flavour, int version, uint32_t n, const uint8_t* msgs, c
     if (fused) {
         for (uint32_t i = 0; i < n; i++) verify_stage_muls(i, a, vb_tab_linear{tabw}, vb_tab_linear{tabw + VB_TAB_WORDS});
     } else {
-        for (uint32_t i = 0; i < n; i++) verify_stage_mul_b(i, a, vb_tab_linear{tabw}, vb_tab_linear{tabw + VB_TAB_WORDS});
-        for (uint32_t i = 0; i < n; i++) verify_stage_mul_a(i, a, vb_tab_linear{tabw});
+        // per-item table storage: the tables live from the table kernel to the ladder kernel
+        std::vector<uint32_t> tabs((size_t)n * 2 * VB_TAB_WORDS);
+        auto t1 = [&](uint32_t i) { return vb_tab_linear{tabs.data() + (size_t)i * 2 * VB_TAB_WORDS}; };
+        auto t2 = [&](uint32_t i) { return vb_tab_linear{tabs.data() + (size_t)i * 2 * VB_TAB_WORDS + VB_TAB_WORDS}; };
+        if (fused == 2) {   // tables + ladder in one kernel (-DPLUME_VERIFY_B_ONE)
+            for (uint32_t i = 0; i < n; i++) verify_stage_mul_b(i, a, t1(i), t2(i));
+        } else {
+            for (uint32_t i = 0; i < n; i++) verify_stage_mul_b1(i, a, t1(i), t2(i));
+            for (uint32_t i = 0; i < n; i++) verify_stage_mul_b2(i, a, t1(i), t2(i));
+        }
+        for (uint32_t i = 0; i < n; i++) verify_stage_mul_a(i, a, t1(i));
     }
     run_binv(a.ws, n, 2 * n, binv_threads);
     for (uint32_t i = 0; i < n; i++) verify_stage_final(i, a);

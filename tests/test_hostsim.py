@@ -154,8 +154,9 @@ def test_sign_verify_pipeline(golden):
         assert len(good) == n - 2
         sel = lambda key: np.ascontiguousarray(o[key][good])
         gm = [msgs[i] for i in good]
-        ok = H.verify_batch(ver, gm, sel("pk"), sel("nullifier"), sel("c"), sel("s"), sel("r_point"), sel("hashed_to_curve_r"))
-        assert ok.all()
+        for fused in (0, 1, 2):   # the shipped kernel split and the two fused forms kept behind build flags
+            ok = H.verify_batch(ver, gm, sel("pk"), sel("nullifier"), sel("c"), sel("s"), sel("r_point"), sel("hashed_to_curve_r"), fused=fused)
+            assert ok.all(), fused
         # negative tests the reference lacks: one flipped bit per item, every field in turn
         fields = ["pk", "nullifier", "c", "s", "r_point", "hashed_to_curve_r"]
         tam = {f: sel(f).copy() for f in fields}

@@ -16,10 +16,10 @@ namespace {
 
 const char* const kStageNames[] = {"sign_fixed", "sign_h2c", "sign_varbase", "sign_final", "verify_h2c",
                                    "verify_muls", "verify_final", "h2c_map", "h2c_out", "binv", "sec1_compress", "sec1_decompress",
-                                   "verify_mul_a", "verify_mul_b", "h2c_witness", "registers"};
+                                   "verify_mul_a", "verify_mul_b", "h2c_witness", "registers", "verify_tab_b"};
 enum Stage { ST_SIGN_FIXED, ST_SIGN_H2C, ST_SIGN_VARBASE, ST_SIGN_FINAL, ST_VERIFY_H2C, ST_VERIFY_MULS,
              ST_VERIFY_FINAL, ST_H2C_MAP, ST_H2C_OUT, ST_BINV, ST_SEC1_COMPRESS, ST_SEC1_DECOMPRESS, ST_VERIFY_MUL_A,
-             ST_VERIFY_MUL_B, ST_H2C_WITNESS, ST_REGISTERS, ST_COUNT };
+             ST_VERIFY_MUL_B, ST_H2C_WITNESS, ST_REGISTERS, ST_VERIFY_TAB_B, ST_COUNT };
 
 struct PendingCopy { void* dst; const void* src; size_t bytes; };
 
@@ -126,8 +126,14 @@ int enqueue_verify(plume_ctx* ctx, verify_args a, cudaStream_t s) {
 #ifdef PLUME_VERIFY_FUSED
     RUN(ST_VERIFY_MULS, launch_verify_muls(a, s));
 #else
-    // two kernels, each with its own register budget: 10 % faster than the fused one (168 registers, 12 warps/SM)
+    // separate kernels, each with its own register budget: the fused one needs 168 registers (12 warps/SM), the two
+    // ladders alone run at 128 (16 warps/SM); 18 % faster in total
+#ifdef PLUME_VERIFY_B_ONE
     RUN(ST_VERIFY_MUL_B, launch_verify_mul_b(a, s));
+#else
+    RUN(ST_VERIFY_TAB_B, launch_verify_tab_b(a, s));
+    RUN(ST_VERIFY_MUL_B, launch_verify_lad_b(a, s));
+#endif
     RUN(ST_VERIFY_MUL_A, launch_verify_mul_a(a, s));
 #endif
     if (int rc = binv(ctx, a.ws, a.n, 2 * a.n, s)) return rc;

@@ -20,6 +20,21 @@ __global__ void __launch_bounds__(PLUME_VM_BLOCK, PLUME_VM_MINBLOCKS) k_verify_m
         verify_stage_mul_b(i, a, vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS},
                            vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS + VB_TAB_WORDS});
 }
+#ifndef PLUME_VB2_MINBLOCKS
+#define PLUME_VB2_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(PLUME_VM_BLOCK, PLUME_VM_MINBLOCKS) k_verify_tab_b(verify_args a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n)
+        verify_stage_mul_b1(i, a, vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS},
+                            vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS + VB_TAB_WORDS});
+}
+__global__ void __launch_bounds__(PLUME_VM_BLOCK, PLUME_VB2_MINBLOCKS) k_verify_lad_b(verify_args a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n)
+        verify_stage_mul_b2(i, a, vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS},
+                            vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS + VB_TAB_WORDS});
+}
 __global__ void __launch_bounds__(PLUME_VM_BLOCK, PLUME_VA_MINBLOCKS) k_verify_mul_a(verify_args a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.n) verify_stage_mul_a(i, a, vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS});
@@ -39,8 +54,16 @@ cudaError_t launch_verify_muls(const verify_args& a, cudaStream_t s) {   // fuse
     k_verify_muls<<<grid_for(a.n, PLUME_VM_BLOCK), PLUME_VM_BLOCK, 0, s>>>(a);
     return cudaGetLastError();
 }
-cudaError_t launch_verify_mul_b(const verify_args& a, cudaStream_t s) {
+cudaError_t launch_verify_mul_b(const verify_args& a, cudaStream_t s) {    // tables + ladder in one kernel (-DPLUME_VERIFY_B_ONE)
     k_verify_mul_b<<<grid_for(a.n, PLUME_VM_BLOCK), PLUME_VM_BLOCK, 0, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_verify_tab_b(const verify_args& a, cudaStream_t s) {
+    k_verify_tab_b<<<grid_for(a.n, PLUME_VM_BLOCK), PLUME_VM_BLOCK, 0, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_verify_lad_b(const verify_args& a, cudaStream_t s) {
+    k_verify_lad_b<<<grid_for(a.n, PLUME_VM_BLOCK), PLUME_VM_BLOCK, 0, s>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_verify_mul_a(const verify_args& a, cudaStream_t s) {

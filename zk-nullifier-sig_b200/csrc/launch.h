@@ -46,6 +46,8 @@ cudaError_t launch_sign_final(const sign_args& a, cudaStream_t s);
 cudaError_t launch_verify_h2c(const verify_args& a, cudaStream_t s);
 cudaError_t launch_verify_muls(const verify_args& a, cudaStream_t s);
 cudaError_t launch_verify_mul_b(const verify_args& a, cudaStream_t s);   // h*s - nul*c  (first: reads the inverted Z of h)
+cudaError_t launch_verify_tab_b(const verify_args& a, cudaStream_t s);   // the two window tables of h*s - nul*c ...
+cudaError_t launch_verify_lad_b(const verify_args& a, cudaStream_t s);   // ... and its double-base ladder
 cudaError_t launch_verify_mul_a(const verify_args& a, cudaStream_t s);   // G*s - pk*c
 cudaError_t launch_verify_final(const verify_args& a, cudaStream_t s);
 cudaError_t launch_h2c_map(const h2c_args& a, cudaStream_t s);

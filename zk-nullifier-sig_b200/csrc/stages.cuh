@@ -530,6 +530,43 @@ PLUME_DEV void verify_stage_mul_b(uint32_t i, const verify_args& a, const Tab& t
     }
     ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, B);
 }
+// verify_stage_mul_b as two kernels: the table pair (b1) and the double-base ladder (b2), so that the ladder, which is
+// where the time goes, is compiled for 4 blocks per SM.  zg travels through WS_KX, the "ladder to do" flag through WS_RY;
+// the rare case of an identity among h, nul (adversarial inputs only) is finished inside b1.
+template <class Tab>
+PLUME_DEV void verify_stage_mul_b1(uint32_t i, const verify_args& a, const Tab& tab1, const Tab& tab2) {
+    aff h = ws_load_affine(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i);
+    ws_store_aff(a.ws, a.n, WS_HX, WS_HY, i, h);
+    st_fe(ws_at(a.ws, a.n, WS_RX, i), fe_set_u32(h.inf));
+    const bool good = a.ok[i] != 0;
+    aff nul;
+    if (good) ld_point_be(nul, a.nullifier + (size_t)i * 64);
+    else nul = aff_generator();
+    const bool both = !h.inf && !nul.inf;
+    st_fe(ws_at(a.ws, a.n, WS_RY, i), fe_set_u32(both ? 1u : 0u));
+    if (both) {
+        st_fe(ws_at(a.ws, a.n, WS_KX, i), vb_build_table_pair(h.x, h.y, tab1, nul.x, nul.y, tab2));
+        return;
+    }
+    sc c = sc_one(), s = sc_one();
+    if (good) {
+        c = ld_sc_be(a.c + (size_t)i * 32);
+        s = ld_sc_be(a.s + (size_t)i * 32);
+    }
+    jac B = jac_add(vb_mul_point(h, s, tab1), vb_mul_point(nul, sc_neg(c), tab1));
+    ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, B);
+}
+template <class Tab>
+PLUME_DEV void verify_stage_mul_b2(uint32_t i, const verify_args& a, const Tab& tab1, const Tab& tab2) {
+    if (ld_fe(ws_at(a.ws, a.n, WS_RY, i)).v[0] == 0) return;   // finished in b1
+    sc c = sc_one(), s = sc_one();
+    if (a.ok[i] != 0) {
+        c = ld_sc_be(a.c + (size_t)i * 32);
+        s = ld_sc_be(a.s + (size_t)i * 32);
+    }
+    jac B = vb_mul2_tab(s, tab1, sc_neg(c), tab2, ld_fe(ws_at(a.ws, a.n, WS_KX, i)));
+    ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, B);
+}
 template <class Tab>
 PLUME_DEV void verify_stage_mul_a(uint32_t i, const verify_args& a, const Tab& tab1) {
     aff pk;
