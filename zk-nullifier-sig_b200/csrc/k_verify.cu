@@ -12,7 +12,7 @@ __global__ void __launch_bounds__(PLUME_VM_BLOCK, PLUME_VM_MINBLOCKS) k_verify_m
                           vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS + VB_TAB_WORDS});
 }
 #ifndef PLUME_VA_MINBLOCKS
-#define PLUME_VA_MINBLOCKS 4
+#define PLUME_VA_MINBLOCKS 6   // k_verify_mul_a per 2^20 items: 4 blocks/SM 19.92 ms, 5: 19.35, 6: 19.45; the ladder of mul_b is best at 4
 #endif
 __global__ void __launch_bounds__(PLUME_VM_BLOCK, PLUME_VM_MINBLOCKS) k_verify_mul_b(verify_args a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

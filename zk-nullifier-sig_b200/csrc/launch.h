@@ -5,10 +5,11 @@
 #include <cuda_runtime.h>
 #include "stages.cuh"
 
-// Variable-base kernels: threads per block, minimum resident blocks per SM (register cap), and where
-// the per-thread window table lives.  Default: a global scratch array (L1/L2 resident, entry = four
-// 128-bit loads) with the registers capped for 4 blocks/SM -- measured 6 % faster than the
-// shared-memory table (3 blocks/SM, no spills); -DPLUME_VB_TAB_SMEM selects the latter.
+// Variable-base kernels: threads per block, minimum resident blocks per SM (register cap), and where the per-thread
+// table lives.  Default: a global scratch array (L1/L2 resident, entry = four 128-bit loads).  Register caps, measured
+// on the B200 per 2^20 items: k_sign_varbase (comb) 4 blocks/SM (128 registers) 30.14 ms, 5 (96) 29.67, 6 (80) 29.43 --
+// the spills of the table-building code cost less than the extra resident warps bring.  -DPLUME_VB_TAB_SMEM selects the
+// shared-memory table of the windowed ladder (3 blocks/SM).
 #ifndef PLUME_VB_BLOCK
 #define PLUME_VB_BLOCK 128
 #endif
@@ -16,7 +17,7 @@
 #ifdef PLUME_VB_TAB_SMEM
 #define PLUME_VB_MINBLOCKS 1
 #else
-#define PLUME_VB_MINBLOCKS 4
+#define PLUME_VB_MINBLOCKS 6
 #endif
 #endif
 #define VB_BLOCK PLUME_VB_BLOCK
