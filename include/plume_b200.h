@@ -58,8 +58,9 @@ typedef struct plume_ctx plume_ctx;
 int plume_version(void);
 
 /* Create a context on CUDA device `device` (ordinal as seen by the CUDA runtime in this
- * process).  Builds the fixed-base table for the generator on the device (one-off, a few ms).
- * `fixed_window_bits` = 0 picks the default; otherwise 4..16.
+ * process).  Builds the fixed-base table for the generator on the device (one-off, ~0.1 s).
+ * `fixed_window_bits` = 0 picks the default (20: a 872 MB table, 13 additions per multiplication); otherwise 4..22
+ * (16 = 64 MiB that stay in the L2, 16 additions).
  * A multi-GPU job is one process (context) per GPU, each given its contiguous range of the
  * batch; nothing is shared between contexts. */
 int plume_ctx_create(plume_ctx** out, int device, int fixed_window_bits);

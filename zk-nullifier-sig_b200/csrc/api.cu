@@ -299,8 +299,10 @@ int plume_ctx_create(plume_ctx** out, int device, int fixed_window_bits) {
     if (e != cudaSuccess || ndev == 0)
         return fail(nullptr, PLUME_E_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
     if (device < 0 || device >= ndev) return fail(nullptr, PLUME_E_NO_DEVICE, "device ordinal out of range");
-    int w = fixed_window_bits ? fixed_window_bits : (int)env_size("PLUME_FIXED_WINDOW", 16);
-    if (w < 4 || w > 16) return fail(nullptr, PLUME_E_ARG, "fixed_window_bits must be in 4..16");
+    // default 20 bits: 13 windows x 2^20 affine points = 872 MB of HBM, 13 additions per fixed-base multiplication
+    // (16 bits: 64 MiB, 16 additions; measured sign_fixed 3.44 -> 2.79 ms and verify_mul_a 19.46 -> 19.03 ms per 2^20 items)
+    int w = fixed_window_bits ? fixed_window_bits : (int)env_size("PLUME_FIXED_WINDOW", 20);
+    if (w < 4 || w > 22) return fail(nullptr, PLUME_E_ARG, "fixed_window_bits must be in 4..22");
     ScopedDevice sd(device);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
