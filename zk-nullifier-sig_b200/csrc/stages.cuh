@@ -164,7 +164,71 @@ PLUME_DEV aff aff_generator() { aff g; g.x = ec_gx(); g.y = ec_gy(); g.inf = 0; 
 // c = SHA-256(enc(G) || enc(pk) || enc(h) || enc(nul) || enc(R) || enc(z))  (V1)
 //   = SHA-256(enc(nul) || enc(R) || enc(z))                                  (V2)
 // rust-k256/src/lib.rs:159-168, rust-k256/src/randomizedsigner.rs:73-89
+// Fixed-layout fast path: when every point is finite the preimage is NP x 33 bytes at known offsets, so the message
+// words are assembled in registers with constant shifts (the byte-stream hasher below goes through a local-memory byte
+// buffer: ~8 000 instructions for the 198 bytes of V1 against ~150 here).
+// W: 16 * ceil((33 NP + 9) / 64) words, zero-initialised.  Point j occupies bytes [33 j, 33 j + 33).
+template <int J>
+PLUME_DEV void challenge_put_point(uint32_t* W, const aff& p) {
+    // the 33-byte string as nine left-aligned big-endian words: P0 = prefix | x[0..2], ..., P8 = last byte of x
+    uint32_t X[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) X[i] = p.x.v[7 - i];
+    uint32_t P[9];
+    P[0] = ((2u + (p.y.v[0] & 1u)) << 24) | (X[0] >> 8);
+#pragma unroll
+    for (int i = 1; i < 8; i++) P[i] = (X[i - 1] << 24) | (X[i] >> 8);
+    P[8] = X[7] << 24;
+    constexpr int off = 33 * J, w0 = off / 4, r = off % 4;
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+        if (r == 0) {
+            W[w0 + k] |= P[k];
+        } else {
+            W[w0 + k] |= P[k] >> (8 * r);
+            W[w0 + k + 1] |= P[k] << (32 - 8 * r);
+        }
+    }
+}
+template <int NP>
+PLUME_DEV sc challenge_finish(uint32_t* W) {
+    constexpr int len = 33 * NP, nblk = (len + 9 + 63) / 64;
+    W[len / 4] |= 0x80u << (24 - 8 * (len % 4));
+    W[16 * nblk - 1] = len * 8;
+    uint32_t st[8];
+    sha256_init(st);
+#pragma unroll
+    for (int b = 0; b < nblk; b++) sha256_compress(st, W + 16 * b);
+    sc c;
+#pragma unroll
+    for (int i = 0; i < 8; i++) c.v[i] = st[7 - i];
+    return c;
+}
+
 PLUME_DEV sc plume_challenge(int version, const aff& pk, const aff& h, const aff& nul, const aff& R, const aff& z) {
+    const bool finite3 = !(nul.inf | R.inf | z.inf);
+    if (version == 1 && finite3 && !(pk.inf | h.inf)) {
+        uint32_t W[64];
+#pragma unroll
+        for (int i = 0; i < 64; i++) W[i] = 0;
+        challenge_put_point<0>(W, aff_generator());
+        challenge_put_point<1>(W, pk);
+        challenge_put_point<2>(W, h);
+        challenge_put_point<3>(W, nul);
+        challenge_put_point<4>(W, R);
+        challenge_put_point<5>(W, z);
+        return challenge_finish<6>(W);
+    }
+    if (version != 1 && finite3) {
+        uint32_t W[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) W[i] = 0;
+        challenge_put_point<0>(W, nul);
+        challenge_put_point<1>(W, R);
+        challenge_put_point<2>(W, z);
+        return challenge_finish<3>(W);
+    }
+    // an identity among the points (1-byte encoding): the general byte-stream path
     sha256_stream s;
     sha256_init(s.st);
     s.fill = 0;
