@@ -1,5 +1,6 @@
-// mul.cuh -- scalar multiplication: fixed-base (generator, precomputed table in HBM/L2) and
-// variable-base (GLV + signed radix-16 windows over a per-thread co-Z table in shared memory).
+// mul.cuh -- scalar multiplication: fixed-base (generator, precomputed window table in HBM), variable-base (GLV +
+// signed radix-16 windows over a per-thread co-Z table in global scratch or shared memory; Straus for two bases) and
+// a signed comb for several scalars on one variable base (end of file).
 //
 // One thread owns one scalar multiplication; all threads of a warp add at the same loop step
 // (fixed windows instead of NAF), so the warp never serialises on data-dependent add/skip

@@ -1,4 +1,4 @@
-// stages.cuh -- per-item bodies of the pipeline stages.  Each kernel in kernels.cu is
+// stages.cuh -- per-item bodies of the pipeline stages.  Each kernel in k_sign.cu / k_verify.cu / k_misc.cu is
 // `i = global thread id; if (i < n) stage_body(i, args)`; the host-sim test build loops the same
 // bodies on the CPU.  Between stages the per-item state lives in HBM as structure-of-arrays
 // "slots" of 32-byte field elements (8 little-endian limbs), so every access is a pair of
@@ -10,13 +10,15 @@
 //   BI batched inversion of the 2 Z's
 //   S2 affine R, pk; pk33; h = H2C(m || pk33) -> Jacobian               [sign_stage_h2c]
 //   BI batched inversion of Z_h
-//   S3 affine h; co-Z table of h; h^r, h^sk -> Jacobian                 [sign_stage_varbase]
+//   S3 affine h; signed-comb table of h; h^r, h^sk -> Jacobian           [sign_stage_varbase_comb]
+//      (windowed ladder per scalar: sign_stage_varbase, -DPLUME_SIGN_WINDOWED / shared-memory table builds)
 //   BI batched inversion of the 2 Z's
 //   S4 affine z, nul; c = SHA-256(...); s = r + c*sk; outputs + status   [sign_stage_final]
 // Verify (rust-k256/src/lib.rs:93-145):
 //   V1 input checks; h = H2C(m || enc(pk)) -> Jacobian                  [verify_stage_h2c]
 //   BI
-//   V2 A = s*G - c*pk ; B = s*h - c*nul -> Jacobian                      [verify_stage_muls]
+//   V2 window tables of h, nul [verify_stage_mul_b1]; B = s*h - c*nul [verify_stage_mul_b2]; A = s*G - c*pk
+//      [verify_stage_mul_a] -> Jacobian   (fused forms verify_stage_mul_b / verify_stage_muls behind build flags)
 //   BI
 //   V3 affine A, B; (V1: compare with r_point, hashed_to_curve_r); c == SHA-256(...) mod n  [verify_stage_final]
 #pragma once
