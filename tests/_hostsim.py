@@ -8,7 +8,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
-LIB = os.path.join(ROOT, "tests", "hostsim", "libplume_hostsim.so")
+EXTRA = [d for d in os.environ.get("PLUME_HOSTSIM_DEFINES", "").split() if d]   # e.g. "PLUME_SQR2 PLUME_MUL2": experiment builds
+LIB = os.path.join(ROOT, "tests", "hostsim", "libplume_hostsim%s.so" % ("_" + "_".join(EXTRA).replace("=", "") if EXTRA else ""))
 CSRC = os.path.join(ROOT, "zk-nullifier-sig_b200", "csrc")
 _lib = None
 
@@ -18,7 +19,7 @@ def lib():
     if _lib is None:
         deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
         if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
-            subprocess.run(["g++", "-O2", "-std=c++17", "-DPLUME_HOSTSIM", "-fPIC", "-shared", "-I", CSRC, "-o", LIB, SRC], check=True)
+            subprocess.run(["g++", "-O2", "-std=c++17", "-DPLUME_HOSTSIM"] + ["-D" + d for d in EXTRA] + ["-fPIC", "-shared", "-I", CSRC, "-o", LIB, SRC], check=True)
         _lib = ctypes.CDLL(LIB)
     return _lib
 
