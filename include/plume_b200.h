@@ -15,10 +15,25 @@
  *   - functions return 0 on success and a negative PLUME_E_* code on failure
  *     (text via plume_last_error); nothing ever aborts or unwinds across this boundary;
  *   - per-item failures are reported in `status[i]` (sign) / `ok[i]` (verify);
- *   - a context is externally synchronised: one batch call at a time per context.
+ *   - a context is externally synchronised: one batch call at a time per context (calls on
+ *     different contexts may run concurrently; plume_last_error(NULL) is per thread).
  *   - `_device` variants take device pointers (16-byte aligned for the 32/64-byte arrays) and
  *     enqueue on the caller's CUDA stream without synchronising; the plain variants take host
- *     pointers, stage them through pinned buffers and return when the results are in place.
+ *     pointers (pinned memory is used in place, pageable memory is staged through pinned buffers
+ *     by a few copy threads) and return when the results are in place.
+ *   - stream ordering: the `_device` entry points share one workspace of their own (separate from
+ *     the host-pointer path's), and every `_device` call is ordered after the previous one by an
+ *     event, whatever streams they were given; a host-pointer call never touches that workspace,
+ *     so it may follow a `_device` call without a synchronisation in between.
+ *   - msg_offsets handed to a host-pointer entry point are checked (non-decreasing, every message
+ *     shorter than 4 GiB; PLUME_E_ARG otherwise); offsets in device memory are the caller's
+ *     responsibility.
+ *   - secrets: the library's own copies of sk and r (device arena, pinned staging arena) are zeroed
+ *     as soon as the chunk that used them has run, and again in plume_ctx_destroy (the reference
+ *     zeroises its witness: javascript/src/lib.rs:64-71,82; rust-arkworks/src/lib.rs:202-214).
+ *     The caller's own buffers are the caller's to clear.  Scalar multiplication is NOT constant
+ *     time (zero windows are skipped, exceptional cases branch): this is a throughput engine for
+ *     batches whose timing is not observable per item; k256's multiplication is constant time.
  *
  * There is no CPU fallback: every entry point fails with PLUME_E_NO_DEVICE / PLUME_E_CUDA when
  * the CUDA device or kernels are unavailable.
@@ -33,7 +48,7 @@
 extern "C" {
 #endif
 
-#define PLUME_ABI_VERSION 1
+#define PLUME_ABI_VERSION 2   /* 2: multi-device contexts, hints argument of the witness call */
 
 /* return codes */
 #define PLUME_OK 0
@@ -65,6 +80,17 @@ int plume_version(void);
  * batch; nothing is shared between contexts. */
 int plume_ctx_create(plume_ctx** out, int device, int fixed_window_bits);
 void plume_ctx_destroy(plume_ctx* ctx);
+
+/* One context over several GPUs of this process (SURVEY.md section 8b "plume_ctx_create(devices[], n)", 8e): one
+ * sub-context and one worker thread per device.  The host-pointer entry points of such a context range-split the batch
+ * -- device g takes items [g n / G, (g+1) n / G) -- run the per-device pipelines concurrently and write the results
+ * straight into the caller's arrays; there is no exchange step.  The `_device` entry points have no meaning on it
+ * (PLUME_E_ARG): use plume_ctx_sub(ctx, g) for device-resident work on GPU g.  Every device builds its own generator
+ * table concurrently unless PLUME_GTAB_BCAST=p2p|nccl asks for device 0's table to be broadcast (peer copies over
+ * NVLink / ncclBroadcast; measured, not faster: DESIGN.md section 6). */
+int plume_ctx_create_multi(plume_ctx** out, const int* devices, int n_devices, int fixed_window_bits);
+int plume_ctx_device_count(const plume_ctx* ctx);          /* 1 for a single-device context */
+plume_ctx* plume_ctx_sub(plume_ctx* ctx, int i);           /* the i-th per-device context (ctx itself when single) */
 
 /* Last error text of this context (or of context creation when ctx is NULL). */
 const char* plume_last_error(const plume_ctx* ctx);
@@ -180,17 +206,27 @@ int plume_ark_verify_batch_device(plume_ctx* ctx, int version, size_t n,
  *   plume_hash_to_curve_witness_batch   for each preimage: u0, u1 = hash_to_field (u: n x 2 x 32, big-endian canonical);
  *                                       gx1_square[2i+k] = 1 when the SSWU map of u_k took x1 (g(x1) is a square), 0 when x2;
  *                                       Q0, Q1 = iso_map(map_to_curve(u_k)), the circuit's x_mapped / y_mapped
- *                                       (q: n x 2 x 64); h = Q0 + Q1 (n x 64) = plume_hash_to_curve_batch's output.
+ *                                       (q: n x 2 x 64); h = Q0 + Q1 (n x 64) = plume_hash_to_curve_batch's output;
+ *                                       hints (n x 2 x 3 x 32, may be NULL): per u_k the circuit's gx1_sqrt, gx2_sqrt, y_pos.
+ *                                       CONVENTION UNPINNED BY THE REFERENCE, declared here: exactly one of g(x1), g(x2) is
+ *                                       a square (Z = -11 is not one); that one's hint is its even square root (RFC 9380
+ *                                       sgn0 = 0), the other hint is 0; y_pos is the even square root of g(x) for the x the
+ *                                       map takes, so the map's y is y_pos or p - y_pos according to sgn0(u_k).
+ *                                       tests/test_circuit_inputs.py checks these against the relations the circuit
+ *                                       enforces (gx1_sqrt^2 = g(x1) or gx2_sqrt^2 = g(x2); y_pos^2 = g(x); the sign rule).
  *   plume_registers_batch               n 32-byte big-endian values -> n x 4 little-endian 64-bit registers, least
  *                                       significant first: scalarToCircuitValue / pointToCircuitValue of
  *                                       circuits/circom/utils.ts:11-17,32-51 (a point is its x then its y).
- * The square-root hints themselves (gx1_sqrt, gx2_sqrt, y_pos) depend on the generator's choice of root and are left to
- * the caller: with u_k, the flag and Q_k they are one modular square root on the host.
  */
 int plume_hash_to_curve_witness_batch(plume_ctx* ctx, size_t n,
                                       const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
-                                      uint8_t* u, uint8_t* q, uint8_t* gx1_square, uint8_t* h);
+                                      uint8_t* u, uint8_t* q, uint8_t* gx1_square, uint8_t* h, uint8_t* hints);
 int plume_registers_batch(plume_ctx* ctx, size_t n, const uint8_t* in32, uint64_t* out4);
+
+/* out[i] = k_i * G for n 32-byte big-endian scalars (taken mod n; 0 gives the identity): public keys from secret keys
+ * (`sk.public_key()`, rust-k256/src/randomizedsigner.rs:53), and the public-key field of the SEC1-DER scalars of the JS
+ * wire form (`SecretKey::from(s).to_sec1_der()`, javascript/src/lib.rs:97-117 -- the host mirrors' sec1_der helpers). */
+int plume_fixed_base_mul_batch(plume_ctx* ctx, size_t n, const uint8_t* scalars, uint8_t* out);
 
 /* Device-pointer variants: all pointers are device memory of the context's GPU, `stream` is a
  * cudaStream_t (passed as void* to keep CUDA headers out of this file).  n must not exceed
@@ -217,7 +253,7 @@ uint64_t plume_ctx_launch_count(const plume_ctx* ctx);
  * stage since profiling was switched on (and their number in *launches), synchronising the
  * context's streams first.  Stage names: "sign_fixed", "sign_h2c", "sign_varbase", "sign_final",
  * "verify_h2c", "verify_mul_a" (G*s - pk*c), "verify_tab_b" + "verify_mul_b" (window tables and ladder of h*s - nul*c), "verify_final", "h2c_map", "h2c_out", "binv",
- * "sec1_compress", "sec1_decompress", "h2c_witness", "registers" ("verify_muls": the two as one kernel, only in -DPLUME_VERIFY_FUSED builds).
+ * "sec1_compress", "sec1_decompress", "h2c_witness", "registers", "fixed_mul".  On a multi-device context: summed over its devices.
  * Returns a negative value for an unknown stage.  set_profiling(ctx, 1) also resets the sums. */
 int plume_ctx_set_profiling(plume_ctx* ctx, int on);
 double plume_ctx_stage_ms(plume_ctx* ctx, const char* stage, uint64_t* launches);
@@ -232,10 +268,16 @@ int plume_measure_imad_rates(plume_ctx* ctx, int iters, double* plain_limb_produ
 
 /* Test hook: element-wise base-field operation on raw limb arrays (n x 8 little-endian 32-bit limbs,
  * any representative below 2^256; host pointers).  op: 0 a*b, 1 a^2, 2 a+b, 3 a-b, 4 1/a, 5 canonical(a),
- * 6 a*b[0] (small), 7 a^((p-3)/4), 8 -a, 9 a^((p+1)/4), 10 a == 0 (mod p).  Results are weakly reduced
+ * 6 a*b[0] (small), 7 a^((p-3)/4), 8 -a, 9 a^((p+1)/4), 10 a == 0 (mod p), 11 8a, 12 2a, 13 4a.  Results are weakly reduced
  * (compare modulo p).  Exists so that the carry-chain assembly of the field layer can be checked in
  * isolation on the GPU (tests/test_gpu_field.py); not part of the reference's interface. */
 int plume_debug_fe_op(plume_ctx* ctx, int op, size_t n, const uint32_t* a, const uint32_t* b, uint32_t* out);
+
+/* Test hook: copies of lane `lane`'s (0 or 1) device I/O arena and pinned staging arena after the context's streams have
+ * drained (host pointers of `cap` bytes each; either may be NULL), so that tests can check that no secret key or nonce
+ * of a finished call survives in the library's own memory. */
+int plume_debug_read_arena(plume_ctx* ctx, int lane, uint8_t* dev_copy, uint8_t* host_copy, size_t cap, size_t* dev_bytes,
+                           size_t* host_bytes);
 
 #ifdef __cplusplus
 }

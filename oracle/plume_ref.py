@@ -313,6 +313,31 @@ def h2c_witness(msg, dst=DST):
     return us, flags, qs, pt_add(qs[0], qs[1])
 
 
+def h2c_sqrt_hints(u):
+    """Square-root hints of the circom hash_to_curve component for one u (circuits/circom/verify_nullifier.circom:21-31:
+    q{0,1}_gx1_sqrt, q{0,1}_gx2_sqrt, q{0,1}_y_pos).  Their generator (npm secp256k1_hash_to_curve_circom) is not in the
+    reference tree, so the convention is the one include/plume_b200.h DECLARES: exactly one of g(x1), g(x2) is a square
+    (Z = -11 is not); that one's hint is its even square root (RFC 9380 sgn0 = 0), the other hint is 0; y_pos is the even
+    square root of g(x) for the x the map takes.  Returns (gx1_sqrt, gx2_sqrt, y_pos) and the relations' inputs
+    (x1, gx1, x2, gx2) so that tests can check what the circuit enforces."""
+    A, Bp = ISO_A, ISO_B
+    tv1 = (Z * Z * pow(u, 4, P) + Z * u * u) % P
+    x1 = Bp * inv(Z * A) % P if tv1 == 0 else (-Bp) * inv(A) % P * (1 + inv(tv1)) % P
+    gx1 = (pow(x1, 3, P) + A * x1 + Bp) % P
+    x2 = Z * u * u % P * x1 % P
+    gx2 = (pow(x2, 3, P) + A * x2 + Bp) % P
+
+    def even_root(v):
+        r = sqrt(v)
+        return r if r % 2 == 0 else P - r
+
+    if is_square(gx1):
+        r = even_root(gx1)
+        return (r, 0, r), (x1, gx1, x2, gx2)
+    r = even_root(gx2)
+    return (0, r, r), (x1, gx1, x2, gx2)
+
+
 def registers(value, bits=64, count=4):
     """circuits/circom/utils.ts:32-51 bigIntToRegisters."""
     assert value < (1 << (bits * count))

@@ -113,8 +113,10 @@ def h2c_witness_batch(msgs, binv_threads=3):
     n = len(msgs)
     blob, offs = _msgs(msgs)
     o = {"u": np.zeros((n, 2, 32), dtype=np.uint8), "q": np.zeros((n, 2, 64), dtype=np.uint8),
-         "gx1_square": np.zeros((n, 2), dtype=np.uint8), "h": np.zeros((n, 64), dtype=np.uint8)}
-    lib().hs_h2c_witness_batch(n, _p(blob), _p(offs), 0, _p(o["u"]), _p(o["q"]), _p(o["gx1_square"]), _p(o["h"]), binv_threads)
+         "gx1_square": np.zeros((n, 2), dtype=np.uint8), "h": np.zeros((n, 64), dtype=np.uint8),
+         "hints": np.zeros((n, 2, 3, 32), dtype=np.uint8)}
+    lib().hs_h2c_witness_batch(n, _p(blob), _p(offs), 0, _p(o["u"]), _p(o["q"]), _p(o["gx1_square"]), _p(o["h"]), binv_threads,
+                               _p(o["hints"]))
     return o
 
 

@@ -49,6 +49,9 @@ void hs_fe_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
         case 7: r = fe_pow_pm3d4(x); break;
         case 8: r = fe_neg(x); break;
         case 9: r = fe_sqrt_cand(x); break;
+        case 11: r = fe_shl<3>(x); break;
+        case 12: r = fe_shl<1>(x); break;
+        case 13: r = fe_shl<2>(x); break;
         default: r = fe_zero();
     }
     memcpy(out, r.v, 32);
@@ -94,8 +97,7 @@ void hs_vb_mul(const uint8_t* p64, const uint8_t* k32, uint8_t* out64) {
     aff p; ld_point_be(p, p64);
     sc k = ld_sc_be(k32);
     uint32_t tabw[VB_TAB_WORDS];
-    vb_tab_linear tab{tabw};
-    jac r = vb_mul_point(p, k, tab);
+    jac r = vb_mul_point(p, k, tabw);
     aff q = r.inf ? aff_infinity() : aff_from_jac_zinv(r, fe_inv(r.z));
     st_point_be(out64, q);
 }
@@ -129,24 +131,23 @@ int hs_sign_batch(int flavour, int comb, int version, uint32_t n, const uint8_t*
     a.sk = sk; a.r = r; a.pk = flavour ? nullptr : pk; a.pk_in = flavour ? pk : nullptr;
     a.nullifier = nul; a.c = c; a.s = s; a.r_point = r_point; a.hashed_to_curve_r = hr;
     a.status = status; a.ws = ws.data(); a.gtab = g_tab.data(); a.gw = gw; a.vbtab = nullptr;
-    uint32_t tabw[VB_TAB_WORDS * 4];
+    std::vector<uint32_t> tabv(VB_ITEM_WORDS);
+    uint32_t* tabw = tabv.data();
     for (uint32_t i = 0; i < n; i++) sign_stage_fixed(i, a);
     run_binv(a.ws, n, 2 * n, binv_threads);
     for (uint32_t i = 0; i < n; i++) sign_stage_h2c(i, a);
     run_binv(a.ws, n, n, binv_threads);
-    // alternate between the two table layouts the kernels can use
     for (uint32_t i = 0; i < n; i++) {
         if (comb) sign_stage_varbase_comb(i, a, tabw);
-        else if (i & 1) sign_stage_varbase(i, a, vb_tab_linear{tabw});
-        else sign_stage_varbase(i, a, vb_tab_strided{tabw + (i & 3), 4});
+        else sign_stage_varbase(i, a, tabw);
     }
     run_binv(a.ws, n, 2 * n, binv_threads);
     for (uint32_t i = 0; i < n; i++) sign_stage_final(i, a);
     return 0;
 }
 
-// fused: 0 the shipped form (table kernel + ladder kernel + G*s - pk*c kernel), 1 everything in one kernel
-// (-DPLUME_VERIFY_FUSED), 2 tables and ladder of h*s - nul*c in one kernel (-DPLUME_VERIFY_B_ONE)
+// the shipped form: table kernel + ladder kernel + G*s - pk*c kernel (`fused` is ignored: the one-kernel forms of
+// round 1 are gone)
 int hs_verify_batch(int flavour, int version, uint32_t n, const uint8_t* msgs, const uint64_t* offs, uint32_t msg_len,
                     const uint8_t* pk, const uint8_t* nul, const uint8_t* c, const uint8_t* s,
                     const uint8_t* r_point, const uint8_t* hr, uint8_t* ok, int gw, uint32_t binv_threads, int fused) {
@@ -156,22 +157,16 @@ int hs_verify_batch(int flavour, int version, uint32_t n, const uint8_t* msgs, c
     a.version = version; a.flavour = flavour; a.n = n; a.msgs.base = msgs; a.msgs.offs = offs; a.msgs.fixed_len = msg_len;
     a.pk = pk; a.nullifier = nul; a.c = c; a.s = s; a.r_point = r_point; a.hashed_to_curve_r = hr;
     a.ok = ok; a.ws = ws.data(); a.gtab = g_tab.data(); a.gw = gw; a.vbtab = nullptr;
-    uint32_t tabw[VB_TAB_WORDS * 4];
+    (void)fused;
     for (uint32_t i = 0; i < n; i++) verify_stage_h2c(i, a);
     run_binv(a.ws, n, n, binv_threads);
-    if (fused) {
-        for (uint32_t i = 0; i < n; i++) verify_stage_muls(i, a, vb_tab_linear{tabw}, vb_tab_linear{tabw + VB_TAB_WORDS});
-    } else {
+    {
         // per-item table storage: the tables live from the table kernel to the ladder kernel
-        std::vector<uint32_t> tabs((size_t)n * 2 * VB_TAB_WORDS);
-        auto t1 = [&](uint32_t i) { return vb_tab_linear{tabs.data() + (size_t)i * 2 * VB_TAB_WORDS}; };
-        auto t2 = [&](uint32_t i) { return vb_tab_linear{tabs.data() + (size_t)i * 2 * VB_TAB_WORDS + VB_TAB_WORDS}; };
-        if (fused == 2) {   // tables + ladder in one kernel (-DPLUME_VERIFY_B_ONE)
-            for (uint32_t i = 0; i < n; i++) verify_stage_mul_b(i, a, t1(i), t2(i));
-        } else {
-            for (uint32_t i = 0; i < n; i++) verify_stage_mul_b1(i, a, t1(i), t2(i));
-            for (uint32_t i = 0; i < n; i++) verify_stage_mul_b2(i, a, t1(i), t2(i));
-        }
+        std::vector<uint32_t> tabs((size_t)n * VB_ITEM_WORDS);
+        auto t1 = [&](uint32_t i) { return tabs.data() + (size_t)i * VB_ITEM_WORDS; };
+        auto t2 = [&](uint32_t i) { return tabs.data() + (size_t)i * VB_ITEM_WORDS + VB_TAB_WORDS; };
+        for (uint32_t i = 0; i < n; i++) verify_stage_mul_b1(i, a, t1(i), t2(i));
+        for (uint32_t i = 0; i < n; i++) verify_stage_mul_b2(i, a, t1(i), t2(i));
         for (uint32_t i = 0; i < n; i++) verify_stage_mul_a(i, a, t1(i));
     }
     run_binv(a.ws, n, 2 * n, binv_threads);
@@ -190,10 +185,10 @@ int hs_h2c_batch(uint32_t n, const uint8_t* msgs, const uint64_t* offs, uint32_t
 }
 
 int hs_h2c_witness_batch(uint32_t n, const uint8_t* msgs, const uint64_t* offs, uint32_t msg_len, uint8_t* u, uint8_t* q,
-                         uint8_t* gx1_square, uint8_t* h, uint32_t binv_threads) {
+                         uint8_t* gx1_square, uint8_t* h, uint32_t binv_threads, uint8_t* hints) {
     std::vector<uint32_t> ws((size_t)WS_SLOTS * n * 8);
     h2cw_args a{};
-    a.n = n; a.msgs.base = msgs; a.msgs.offs = offs; a.msgs.fixed_len = msg_len; a.u = u; a.q = q; a.gx1_square = gx1_square; a.h = h;
+    a.n = n; a.msgs.base = msgs; a.msgs.offs = offs; a.msgs.fixed_len = msg_len; a.u = u; a.q = q; a.gx1_square = gx1_square; a.h = h; a.hints = hints;
     a.ws = ws.data();
     for (uint32_t i = 0; i < n; i++) h2cw_stage_map(i, a);
     run_binv(a.ws, n, 2 * n, binv_threads);

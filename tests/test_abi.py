@@ -26,7 +26,7 @@ def test_header_symbols_exported():
     for n in names:
         assert hasattr(lib, n), "libplume_b200.so does not export " + n
     assert set(names) == set(plume_b200.SYMBOLS), "python binding and header disagree"
-    assert plume_b200.load().plume_version() == 1
+    assert plume_b200.load().plume_version() == 2
 
 
 def test_no_cpu_fallback():

@@ -1,8 +1,10 @@
 """the intermediates of hash_to_curve and the 4 x 64-bit register form the circom circuit consumes
 (circuits/circom/verify_nullifier.circom:21-31, circuits/circom/utils.ts:11-51).  What the reference pins is checked
 against it: u0 of the empty message (rust-arkworks/src/secp256k1/tests.rs:126), h of "abc", the 62-byte preimage and the
-fixed signing vector; the rest against the Python restatement of RFC 9380.  The square-root hints themselves are produced
-by an npm package that is not in the reference tree: parity unpinned, left to the caller (include/plume_b200.h)."""
+fixed signing vector; the rest against the Python restatement of RFC 9380.  The square-root hints (gx1_sqrt, gx2_sqrt, y_pos)
+are produced in the reference by an npm package that is not in its tree: their convention is DECLARED by
+include/plume_b200.h (even roots, 0 where no root exists) and checked here against the algebraic relations the circuit
+enforces -- "convention unpinned by the reference"."""
 import random
 
 import numpy as np
@@ -33,6 +35,19 @@ def _check(o, msgs, golden):
             assert int(o["gx1_square"][i, k]) == flags[k], (i, k)
             assert bytes(o["q"][i, k]) == _pt64(qs[k]), (i, k)
         assert bytes(o["h"][i]) == _pt64(h), i
+        for k in range(2):   # the square-root hints: declared convention + the relations the circuit enforces
+            want, (x1, gx1, x2, gx2) = R.h2c_sqrt_hints(us[k])
+            got = [int.from_bytes(bytes(o["hints"][i, k, j]), "big") for j in range(3)]
+            assert got == list(want), (i, k)
+            g1s, g2s, ypos = got
+            if flags[k]:
+                assert g1s * g1s % R.P == gx1 and g2s == 0
+            else:
+                assert g2s * g2s % R.P == gx2 and g1s == 0 and not R.is_square(gx1)
+            x, y = R.map_to_curve_sswu(us[k])
+            assert x == (x1 if flags[k] else x2) and ypos % 2 == 0 and ypos < R.P
+            assert ypos * ypos % R.P == (pow(x, 3, R.P) + R.ISO_A * x + R.ISO_B) % R.P
+            assert y in (ypos, R.P - ypos) and y % 2 == us[k] % 2
     # pinned by the reference
     assert bytes(o["h"][0]).hex() == golden["h2c_abc"]["x"] + golden["h2c_abc"]["y"]
     assert int.from_bytes(bytes(o["u"][1, 0]), "big") == int(golden["h2c_empty"]["u0_dec"])

@@ -23,7 +23,10 @@ def test_field_ops(gpu_ctx):
     rnd = random.Random(12)
     C = 2**32 + 977
     edge = [0, 1, 2, P - 1, P, P + 1, 2**256 - 1, 2**256 - 2, P - 2, 2**255, C, C - 1, C + 1, 2**256 - C, 2**256 - C - 1, 0xFFFFFFFF,
-            2**224 - 1, (2**256 - 1) ^ (2**128), (1 << 256) - (1 << 224), 2**64 - 1, 2**64, (2**256 - 1) ^ 0xFFFFFFFF, 977, 2**33]
+            2**224 - 1, (2**256 - 1) ^ (2**128), (1 << 256) - (1 << 224), 2**64 - 1, 2**64, (2**256 - 1) ^ 0xFFFFFFFF, 977, 2**33,
+            # shifted left by 1..3 these leave limb 1 (and limbs 2..7) all ones, so that folding the bits shifted out ripples
+            (2**256 - 1) >> 1, (2**256 - 1) >> 2, (2**256 - 1) >> 3, (7 << 253) | ((2**253 - 1) ^ 0x1FFFFFFF), (3 << 254) | (2**254 - 2**29),
+            (1 << 255) | (2**255 - 2**31), (7 << 253) | (2**253 - 2**29), (7 << 253) | (2**61 - 2**29)]
     A, B = [], []
     for x in edge:           # every edge value against every edge value
         for y in edge:
@@ -43,6 +46,7 @@ def test_field_ops(gpu_ctx):
     neg = _ints(gpu_ctx.debug_fe_op(8, a, b))
     nrm = _ints(gpu_ctx.debug_fe_op(5, a, b))
     isz = _ints(gpu_ctx.debug_fe_op(10, a, b))
+    sh = {k: _ints(gpu_ctx.debug_fe_op(op, a, b)) for k, op in ((1, 12), (2, 13), (3, 11))}
     for i, (x, y) in enumerate(zip(A, B)):
         assert mul[i] % P == x * y % P, ("mul", hex(x), hex(y))
         assert add[i] % P == (x + y) % P, ("add", hex(x), hex(y))
@@ -51,6 +55,8 @@ def test_field_ops(gpu_ctx):
         assert neg[i] % P == (-x) % P, ("neg", hex(x))
         assert nrm[i] == x % P, ("norm", hex(x))
         assert isz[i] == (1 if x % P == 0 else 0)
+        for k in (1, 2, 3):
+            assert sh[k][i] % P == (x << k) % P, ("shl", k, hex(x))
     for k in (0, 1, 2, 3, 8, 11, 1771, 65535, 65536, 2**32 - 1):
         kb = _limbs([k] * len(A))
         ms = _ints(gpu_ctx.debug_fe_op(6, a, kb))

@@ -35,6 +35,8 @@ def test_field_arithmetic_limb_level():
         assert H.fe_op(1, a) % P == a * a % P
         assert H.fe_op(5, a) == a % P
         assert H.fe_op(8, a) % P == (-a) % P
+        for k, op in ((1, 12), (2, 13), (3, 11)):
+            assert H.fe_op(op, a) % P == (a << k) % P
         for k in (0, 1, 2, 3, 8, 11, 1771, 65535, 65536):
             assert H.fe_op(6, a, k) % P == a * k % P
         assert bool(H.lib().hs_fe_is_zero(H.limbs(a))) == (a % P == 0)
@@ -129,7 +131,7 @@ def test_h2c_pipeline(golden):
 def _check_sign_verify(ver, msgs, sks, rs, golden=None):
     skb = b"".join(x.to_bytes(32, "big") for x in sks); rb = b"".join(x.to_bytes(32, "big") for x in rs)
     want = c_oracle.sign_batch(ver, msgs, skb, rb, threads=2)
-    for comb in (True, False):   # the shipped signed comb, and the windowed ladder kept for the shared-memory build
+    for comb in (True, False):   # the shipped signed comb, and the windowed ladder kept behind -DPLUME_SIGN_WINDOWED
         got = H.sign_batch(ver, msgs, skb, rb, gw=8, binv_threads=5, comb=comb)
         for k in ("status", "pk", "nullifier", "c", "s", "r_point", "hashed_to_curve_r"):
             assert np.array_equal(got[k], want[k]), (k, comb)
@@ -154,9 +156,8 @@ def test_sign_verify_pipeline(golden):
         assert len(good) == n - 2
         sel = lambda key: np.ascontiguousarray(o[key][good])
         gm = [msgs[i] for i in good]
-        for fused in (0, 1, 2):   # the shipped kernel split and the two fused forms kept behind build flags
-            ok = H.verify_batch(ver, gm, sel("pk"), sel("nullifier"), sel("c"), sel("s"), sel("r_point"), sel("hashed_to_curve_r"), fused=fused)
-            assert ok.all(), fused
+        ok = H.verify_batch(ver, gm, sel("pk"), sel("nullifier"), sel("c"), sel("s"), sel("r_point"), sel("hashed_to_curve_r"))
+        assert ok.all()
         # negative tests the reference lacks: one flipped bit per item, every field in turn
         fields = ["pk", "nullifier", "c", "s", "r_point", "hashed_to_curve_r"]
         tam = {f: sel(f).copy() for f in fields}

@@ -62,9 +62,27 @@ PLUME_POINTFN jac jac_dbl(jac p) {
     fe D = fe_dbl(fe_sub(fe_sub(t, A), C));  // 2*((X+B)^2 - A - C)  (t dead)
     fe E = fe_add(fe_dbl(A), A);             // 3*A                  (A dead)
     r.x = fe_sub(EC_SQR(E), fe_dbl(D));      // E^2 - 2*D
-    fe C8 = fe_dbl(fe_dbl(fe_dbl(C)));
+    fe C8 = fe_shl<3>(C);
     r.y = fe_sub(EC_MUL(E, fe_sub(D, r.x)), C8);
     r.inf = 0;
+    return r;
+}
+
+// The same doubling for the ladders: no test of the identity flag.  The identity is always stored as (0, 0, 0) with the
+// flag set, and the formulas map (0, 0, 0) to (0, 0, 0), so the flag is simply carried along (the generic version above
+// compiles its early return into selects over all 24 result registers).
+PLUME_POINTFN jac jac_dbl_fast(jac p) {
+    jac r;
+    r.z = fe_dbl(EC_MUL(p.y, p.z));
+    fe A = EC_SQR(p.x);
+    fe B = EC_SQR(p.y);
+    fe t = EC_SQR(fe_add(p.x, B));
+    fe C = EC_SQR(B);
+    fe D = fe_dbl(fe_sub(fe_sub(t, A), C));
+    fe E = fe_add(fe_dbl(A), A);
+    r.x = fe_sub(EC_SQR(E), fe_dbl(D));
+    r.y = fe_sub(EC_MUL(E, fe_sub(D, r.x)), fe_shl<3>(C));
+    r.inf = p.inf;
     return r;
 }
 
@@ -87,6 +105,60 @@ PLUME_POINTFN jac jac_add_aff(jac p, fe qx, fe qy, uint32_t qinf) {
     r.x = fe_sub(fe_sub(EC_SQR(R), H3), fe_dbl(V));
     r.y = fe_sub(EC_MUL(R, fe_sub(V, r.x)), EC_MUL(p.y, H3));
     r.inf = 0;
+    return r;
+}
+
+// P + Q for the ladders: Q affine and finite (a table entry), P anything.  The only test on the common path is H == 0,
+// which the identity (0, 0, 0) also satisfies (H = qx * 0 - 0), so the identity operand, P = Q and P = -Q all leave
+// through the same rare branch.
+PLUME_POINTFN jac jac_add_aff_fast(jac p, fe qx, fe qy) {
+    fe z2 = EC_SQR(p.z);
+    fe H = fe_sub(EC_MUL(qx, z2), p.x);
+    fe R = fe_sub(EC_MUL(qy, EC_MUL(p.z, z2)), p.y);
+    if (fe_is_zero(H)) {
+        if (p.inf) { jac r; r.x = qx; r.y = qy; r.z = fe_one(); r.inf = 0; return r; }
+        if (fe_is_zero(R)) return jac_dbl(p);
+        return jac_infinity();
+    }
+    jac r;
+    r.z = EC_MUL(p.z, H);
+    fe H2 = EC_SQR(H);
+    fe H3 = EC_MUL(H, H2);
+    fe V = EC_MUL(p.x, H2);
+    r.x = fe_sub(fe_sub(EC_SQR(R), H3), fe_dbl(V));
+    r.y = fe_sub(EC_MUL(R, fe_sub(V, r.x)), EC_MUL(p.y, H3));
+    r.inf = 0;
+    return r;
+}
+
+// Conjugate addition: P + Q and P - Q for Q affine, 9M + 4S for the pair instead of 2 x (8M + 3S), and both results come
+// out with the SAME Z (= Z_P * H), which halves the work of bringing a table to a common denominator.  Only for operands
+// known to be finite with P != +-Q (the signed-comb table: odd combinations of the teeth of a prime-order point).
+struct jac_pair { fe xs, ys, xd, yd, z; };   // sum (xs, ys), difference (xd, yd), shared z
+PLUME_DEV jac_pair jac_conj_add_aff(const fe& px, const fe& py, const fe& pz, bool pz_is_one, const fe& qx, const fe& qy) {
+    fe H, S2;
+    jac_pair r;
+    if (pz_is_one) {
+        H = fe_sub(qx, px);
+        S2 = qy;
+        r.z = H;
+    } else {
+        fe z2 = fe_sqr(pz);
+        H = fe_sub(fe_mul(qx, z2), px);
+        S2 = fe_mul(qy, fe_mul(pz, z2));
+        r.z = fe_mul(pz, H);
+    }
+    fe H2 = fe_sqr(H);
+    fe H3 = fe_mul(H, H2);
+    fe V = fe_mul(px, H2);
+    fe V2 = fe_dbl(V);
+    fe YH3 = fe_mul(py, H3);
+    fe Rs = fe_sub(S2, py);                 // S2 - Y1
+    fe Rd = fe_neg(fe_add(S2, py));         // -S2 - Y1
+    r.xs = fe_sub(fe_sub(fe_sqr(Rs), H3), V2);
+    r.ys = fe_sub(fe_mul(Rs, fe_sub(V, r.xs)), YH3);
+    r.xd = fe_sub(fe_sub(fe_sqr(Rd), H3), V2);
+    r.yd = fe_sub(fe_mul(Rd, fe_sub(V, r.xd)), YH3);
     return r;
 }
 

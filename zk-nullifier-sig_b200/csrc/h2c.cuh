@@ -66,24 +66,84 @@ PLUME_DEV fe h2c_os2ip_mod_p(const uint32_t* w12) {
     return fe_norm(fe_reduce512(T));
 }
 
+// b_0 for the 65-byte preimage every PLUME call hashes (32-byte message || 33-byte SEC1 public key, or a 65-byte record
+// handed to the hash_to_curve entry point): the stream after the Z_pad block is
+//     preimage(65) || 00 60 00 || DST'(50)   = 118 bytes = two blocks with the padding,
+// so the 32 message words are assembled in registers at constant offsets -- no byte buffer in local memory, no per-byte
+// bookkeeping (the byte-stream hasher below spends ~8 000 instructions on these 118 bytes; this path ~150 plus the two
+// compressions).  M: the preimage as 16 big-endian words, last: its 65th byte.
+PLUME_DEV void h2c_b0_fixed65(uint32_t* b0, const uint32_t* M, uint32_t last) {
+    uint32_t st[8], w[16];
+    sha256_init_after_zero_block(st);
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = M[i];
+    sha256_compress(st, w);
+    // second block: byte 64 of the preimage, 00 60 00, DST' (50 bytes at offsets 4..53), 0x80 at 54, zeros, bit length
+    w[0] = (last << 24) | 0x006000u;
+#pragma unroll
+    for (int i = 1; i < 16; i++) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int o = 4 * i + b - 4;   // offset inside DST'
+            uint32_t byte = (o < 50) ? h2c_dst_prime(o) : (o == 50 ? 0x80u : 0u);
+            v = (v << 8) | byte;
+        }
+        w[i] = v;
+    }
+    w[15] = (64 + 118) * 8;
+    sha256_compress(st, w);
+#pragma unroll
+    for (int i = 0; i < 8; i++) b0[i] = st[i];
+}
+
+// 32 or 65 consecutive bytes -> big-endian words (word loads when the address allows it, byte loads otherwise)
+template <int NW>
+PLUME_DEV void h2c_load_be_words(uint32_t* W, const uint8_t* p) {
+#ifndef PLUME_HOSTSIM
+    if ((reinterpret_cast<uintptr_t>(p) & 3) == 0) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+#pragma unroll
+        for (int i = 0; i < NW; i++) W[i] = bswap32(__ldg(q + i));
+        return;
+    }
+#endif
+#pragma unroll
+    for (int i = 0; i < NW; i++)
+        W[i] = ((uint32_t)p[4 * i] << 24) | ((uint32_t)p[4 * i + 1] << 16) | ((uint32_t)p[4 * i + 2] << 8) | p[4 * i + 3];
+}
+
 // uniform_bytes = expand_message_xmd(msg || tail, DST, 96) then two field elements.
 // The hashed stream is  Z_pad(64) || msg(len) || extra(nextra) || 0x00 0x60 || 0x00 || DST'.
 // `extra` is the SEC1 encoding of pk that PLUME appends to the message (33 bytes, or 1 byte for
 // the identity, or nothing for the plain hash_to_curve entry point).
 PLUME_DEV void h2c_hash_to_field(fe& u0, fe& u1, const uint8_t* msg, uint32_t len, const uint8_t* extra, uint32_t nextra) {
-    sha256_stream s;
-    sha256_init_after_zero_block(s.st);
-    s.fill = 0;
-    s.total = 64;
-    sha256_stream_bytes(s, msg, len);
-    sha256_stream_bytes(s, extra, nextra);
-    sha256_stream_byte(s, 0x00);
-    sha256_stream_byte(s, 0x60);  // len_in_bytes = 96
-    sha256_stream_byte(s, 0x00);
-#pragma unroll 1
-    for (int i = 0; i < 50; i++) sha256_stream_byte(s, h2c_dst_prime(i));
     uint32_t b0[8];
-    sha256_stream_final(s, b0);
+    if (len == 32 && nextra == 33) {          // m || enc33(pk): the shape of every BASELINE config
+        uint32_t M[16];
+        h2c_load_be_words<8>(M, msg);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            M[8 + i] = ((uint32_t)extra[4 * i] << 24) | ((uint32_t)extra[4 * i + 1] << 16) | ((uint32_t)extra[4 * i + 2] << 8) | extra[4 * i + 3];
+        h2c_b0_fixed65(b0, M, extra[32]);
+    } else if (len == 65 && nextra == 0) {    // a caller-assembled 65-byte preimage (plume_hash_to_curve_batch)
+        uint32_t M[16];
+        h2c_load_be_words<16>(M, msg);
+        h2c_b0_fixed65(b0, M, msg[64]);
+    } else {
+        sha256_stream s;
+        sha256_init_after_zero_block(s.st);
+        s.fill = 0;
+        s.total = 64;
+        sha256_stream_bytes(s, msg, len);
+        sha256_stream_bytes(s, extra, nextra);
+        sha256_stream_byte(s, 0x00);
+        sha256_stream_byte(s, 0x60);  // len_in_bytes = 96
+        sha256_stream_byte(s, 0x00);
+#pragma unroll 1
+        for (int i = 0; i < 50; i++) sha256_stream_byte(s, h2c_dst_prime(i));
+        sha256_stream_final(s, b0);
+    }
     uint32_t ub[24];
     h2c_hash_bi(ub, b0, 1);
     uint32_t x[8];
@@ -117,7 +177,9 @@ PLUME_DEV bool h2c_sqrt_ratio(fe& y, const fe& u, const fe& v) {
 }
 
 // simplified SWU on E': y^2 = x^3 + A'x + B' (RFC 9380 F.2, straight line); x = xn / xd
-PLUME_DEV bool h2c_map_sswu(fe& xn, fe& xd, fe& y, const fe& u) {   // returns is_square(g(x1)): which candidate x was taken
+// root (optional): the square root of g(x) the map found, before the sign is matched to sgn0(u) -- sqrt(g(x1)) when g(x1) is a
+// square, u^3 Z sqrt(Z g(x1)) = sqrt(g(x2)) otherwise (the circuit-input hints of SURVEY.md 8f-4 are made from it)
+PLUME_DEV bool h2c_map_sswu(fe& xn, fe& xd, fe& y, const fe& u, fe* root = nullptr) {   // returns is_square(g(x1)): which candidate x was taken
     const fe A = h2c_iso_a();
     fe tv1 = fe_neg(fe_mul_small(fe_sqr(u), 11));  // Z * u^2, Z = -11
     fe tv2 = fe_add(fe_sqr(tv1), tv1);
@@ -138,6 +200,7 @@ PLUME_DEV bool h2c_map_sswu(fe& xn, fe& xd, fe& y, const fe& u) {   // returns i
     fe yy = fe_mul(fe_mul(tv1, u), y1);
     x = fe_cmov(x, tv3, is_gx1_square);
     yy = fe_cmov(yy, y1, is_gx1_square);
+    if (root) *root = yy;
     bool e1 = fe_is_odd(u) == fe_is_odd(yy);
     y = fe_cmov(fe_neg(yy), yy, e1);
     xn = x;

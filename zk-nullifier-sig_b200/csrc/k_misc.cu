@@ -17,6 +17,14 @@ __global__ void __launch_bounds__(128) k_h2cw_out(h2cw_args a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.n) h2cw_stage_out(i, a);
 }
+__global__ void __launch_bounds__(128) k_fbmul_map(fbmul_args a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) fbmul_stage_map(i, a);
+}
+__global__ void __launch_bounds__(128) k_fbmul_out(fbmul_args a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) fbmul_stage_out(i, a);
+}
 __global__ void __launch_bounds__(256) k_registers(uint32_t n, const uint8_t* in32, uint64_t* out4) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) registers_body(i, in32, out4);
@@ -70,6 +78,9 @@ __global__ void __launch_bounds__(128) k_debug_fe_op(int op, uint32_t n, const u
         case 8: r = fe_neg(x); break;
         case 9: r = fe_sqrt_cand(x); break;
         case 10: r = fe_set_u32(fe_is_zero(x) ? 1u : 0u); break;
+        case 11: r = fe_shl<3>(x); break;
+        case 12: r = fe_shl<1>(x); break;
+        case 13: r = fe_shl<2>(x); break;
         default: r = fe_zero();
     }
     st_fe(out + (size_t)i * 8, r);
@@ -145,6 +156,11 @@ cudaError_t launch_h2cw(int stage, const h2cw_args& a, cudaStream_t s) {
     if (stage == 0) k_h2cw_map<<<grid_for(a.n, 128), 128, 0, s>>>(a);
     else if (stage == 1) k_h2cw_sum<<<grid_for(a.n, 128), 128, 0, s>>>(a);
     else k_h2cw_out<<<grid_for(a.n, 128), 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_fbmul(int stage, const fbmul_args& a, cudaStream_t s) {
+    if (stage == 0) k_fbmul_map<<<grid_for(a.n, 128), 128, 0, s>>>(a);
+    else k_fbmul_out<<<grid_for(a.n, 128), 128, 0, s>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_registers(uint32_t n, const uint8_t* in32, uint64_t* out4, cudaStream_t s) {

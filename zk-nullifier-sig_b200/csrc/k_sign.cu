@@ -10,12 +10,11 @@ __global__ void __launch_bounds__(128, PLUME_H2C_MINBLOCKS) k_sign_h2c(sign_args
     if (i < a.n) sign_stage_h2c(i, a);
 }
 __global__ void __launch_bounds__(VB_BLOCK, PLUME_VB_MINBLOCKS) k_sign_varbase(sign_args a) {
-    extern __shared__ uint32_t vb_smem[];
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-#if defined(PLUME_VB_TAB_SMEM) || defined(PLUME_SIGN_WINDOWED)
-    if (i < a.n) sign_stage_varbase(i, a, VB_TAB(a, i));          // windowed ladder per scalar (132 doublings each)
+#ifdef PLUME_SIGN_WINDOWED
+    if (i < a.n) sign_stage_varbase(i, a, a.vbtab + (size_t)i * VB_ITEM_WORDS);          // windowed ladder per scalar (132 doublings each)
 #else
-    if (i < a.n) sign_stage_varbase_comb(i, a, a.vbtab + (size_t)i * COMB_AREA_WORDS);   // signed comb, shared teeth
+    if (i < a.n) sign_stage_varbase_comb(i, a, a.vbtab + (size_t)i * VB_ITEM_WORDS);     // signed comb, shared teeth
 #endif
 }
 __global__ void __launch_bounds__(128) k_sign_final(sign_args a) {
@@ -34,14 +33,11 @@ cudaError_t launch_sign_h2c(const sign_args& a, cudaStream_t s) {
     return cudaGetLastError();
 }
 cudaError_t launch_sign_varbase(const sign_args& a, cudaStream_t s) {
-    k_sign_varbase<<<grid_for(a.n, VB_BLOCK), VB_BLOCK, VB_SMEM_BYTES, s>>>(a);
+    k_sign_varbase<<<grid_for(a.n, VB_BLOCK), VB_BLOCK, 0, s>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_sign_final(const sign_args& a, cudaStream_t s) {
     k_sign_final<<<grid_for(a.n, 128), 128, 0, s>>>(a);
     return cudaGetLastError();
 }
-cudaError_t kernels_init_sign() {
-    if (VB_SMEM_BYTES == 0) return cudaSuccess;
-    return cudaFuncSetAttribute(k_sign_varbase, cudaFuncAttributeMaxDynamicSharedMemorySize, VB_SMEM_BYTES);
-}
+cudaError_t kernels_init_sign() { return cudaSuccess; }

@@ -5,24 +5,8 @@ __global__ void __launch_bounds__(128, PLUME_H2C_MINBLOCKS) k_verify_h2c(verify_
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.n) verify_stage_h2c(i, a);
 }
-#ifdef PLUME_VERIFY_FUSED   // everything of V2 in one kernel: 168 registers, 12 warps/SM (the first layout; 17 % slower)
-__global__ void __launch_bounds__(PLUME_VM_BLOCK, PLUME_VM_MINBLOCKS) k_verify_muls(verify_args a) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < a.n)
-        verify_stage_muls(i, a, vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS},
-                          vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS + VB_TAB_WORDS});
-}
-#endif
 #ifndef PLUME_VA_MINBLOCKS
 #define PLUME_VA_MINBLOCKS 6   // k_verify_mul_a per 2^20 items: 4 blocks/SM 19.92 ms, 5: 19.35, 6: 19.45; the ladder of mul_b is best at 4
-#endif
-#ifdef PLUME_VERIFY_B_ONE   // tables and ladder of h*s - nul*c in one kernel: 168 registers (9 % slower than the two below)
-__global__ void __launch_bounds__(PLUME_VM_BLOCK, PLUME_VM_MINBLOCKS) k_verify_mul_b(verify_args a) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < a.n)
-        verify_stage_mul_b(i, a, vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS},
-                           vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS + VB_TAB_WORDS});
-}
 #endif
 #ifndef PLUME_VB2_MINBLOCKS
 #define PLUME_VB2_MINBLOCKS 4
@@ -30,18 +14,16 @@ __global__ void __launch_bounds__(PLUME_VM_BLOCK, PLUME_VM_MINBLOCKS) k_verify_m
 __global__ void __launch_bounds__(PLUME_VM_BLOCK, PLUME_VM_MINBLOCKS) k_verify_tab_b(verify_args a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.n)
-        verify_stage_mul_b1(i, a, vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS},
-                            vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS + VB_TAB_WORDS});
+        verify_stage_mul_b1(i, a, a.vbtab + (size_t)i * VB_ITEM_WORDS, a.vbtab + (size_t)i * VB_ITEM_WORDS + VB_TAB_WORDS);
 }
 __global__ void __launch_bounds__(PLUME_VM_BLOCK, PLUME_VB2_MINBLOCKS) k_verify_lad_b(verify_args a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.n)
-        verify_stage_mul_b2(i, a, vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS},
-                            vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS + VB_TAB_WORDS});
+        verify_stage_mul_b2(i, a, a.vbtab + (size_t)i * VB_ITEM_WORDS, a.vbtab + (size_t)i * VB_ITEM_WORDS + VB_TAB_WORDS);
 }
 __global__ void __launch_bounds__(PLUME_VM_BLOCK, PLUME_VA_MINBLOCKS) k_verify_mul_a(verify_args a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < a.n) verify_stage_mul_a(i, a, vb_tab_linear{a.vbtab + (size_t)i * 2 * VB_TAB_WORDS});
+    if (i < a.n) verify_stage_mul_a(i, a, a.vbtab + (size_t)i * VB_ITEM_WORDS);
 }
 __global__ void __launch_bounds__(128) k_verify_final(verify_args a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -54,18 +36,6 @@ cudaError_t launch_verify_h2c(const verify_args& a, cudaStream_t s) {
     k_verify_h2c<<<grid_for(a.n, 128), 128, 0, s>>>(a);
     return cudaGetLastError();
 }
-#ifdef PLUME_VERIFY_FUSED
-cudaError_t launch_verify_muls(const verify_args& a, cudaStream_t s) {
-    k_verify_muls<<<grid_for(a.n, PLUME_VM_BLOCK), PLUME_VM_BLOCK, 0, s>>>(a);
-    return cudaGetLastError();
-}
-#endif
-#ifdef PLUME_VERIFY_B_ONE
-cudaError_t launch_verify_mul_b(const verify_args& a, cudaStream_t s) {
-    k_verify_mul_b<<<grid_for(a.n, PLUME_VM_BLOCK), PLUME_VM_BLOCK, 0, s>>>(a);
-    return cudaGetLastError();
-}
-#endif
 cudaError_t launch_verify_tab_b(const verify_args& a, cudaStream_t s) {
     k_verify_tab_b<<<grid_for(a.n, PLUME_VM_BLOCK), PLUME_VM_BLOCK, 0, s>>>(a);
     return cudaGetLastError();

@@ -5,29 +5,17 @@
 #include <cuda_runtime.h>
 #include "stages.cuh"
 
-// Variable-base kernels: threads per block, minimum resident blocks per SM (register cap), and where the per-thread
-// table lives.  Default: a global scratch array (L1/L2 resident, entry = four 128-bit loads).  Register caps, measured
-// on the B200 per 2^20 items: k_sign_varbase (comb) 4 blocks/SM (128 registers) 30.14 ms, 5 (96) 29.67, 6 (80) 29.43 --
-// the spills of the table-building code cost less than the extra resident warps bring.  -DPLUME_VB_TAB_SMEM selects the
-// shared-memory table of the windowed ladder (3 blocks/SM).
+// Variable-base kernels: threads per block and minimum resident blocks per SM (register cap).  The per-thread tables live
+// in a global scratch array (L1/L2 resident, one 128-byte line per entry).  Register caps, measured on the B200 per 2^20
+// items (round 1): k_sign_varbase 4 blocks/SM (128 registers) 30.14 ms, 5 (96) 29.67, 6 (80) 29.43 -- the spills of the
+// table-building code cost less than the extra resident warps bring.
 #ifndef PLUME_VB_BLOCK
 #define PLUME_VB_BLOCK 128
 #endif
 #ifndef PLUME_VB_MINBLOCKS
-#ifdef PLUME_VB_TAB_SMEM
-#define PLUME_VB_MINBLOCKS 1
-#else
 #define PLUME_VB_MINBLOCKS 6
 #endif
-#endif
 #define VB_BLOCK PLUME_VB_BLOCK
-#ifndef PLUME_VB_TAB_SMEM
-#define VB_SMEM_BYTES 0
-#define VB_TAB(a, i) vb_tab_linear{(a).vbtab + (size_t)(i) * 2 * VB_TAB_WORDS}
-#else
-#define VB_SMEM_BYTES (VB_TAB_WORDS * 4 * VB_BLOCK)
-#define VB_TAB(a, i) vb_tab_strided{vb_smem + threadIdx.x, VB_BLOCK}
-#endif
 // hash-to-curve kernels: register cap (blocks of 128 threads per SM)
 #ifndef PLUME_H2C_MINBLOCKS
 #define PLUME_H2C_MINBLOCKS 4
@@ -45,15 +33,14 @@ cudaError_t launch_sign_h2c(const sign_args& a, cudaStream_t s);
 cudaError_t launch_sign_varbase(const sign_args& a, cudaStream_t s);
 cudaError_t launch_sign_final(const sign_args& a, cudaStream_t s);
 cudaError_t launch_verify_h2c(const verify_args& a, cudaStream_t s);
-cudaError_t launch_verify_muls(const verify_args& a, cudaStream_t s);
-cudaError_t launch_verify_mul_b(const verify_args& a, cudaStream_t s);   // h*s - nul*c  (first: reads the inverted Z of h)
-cudaError_t launch_verify_tab_b(const verify_args& a, cudaStream_t s);   // the two window tables of h*s - nul*c ...
+cudaError_t launch_verify_tab_b(const verify_args& a, cudaStream_t s);   // the two window tables of h*s - nul*c (first: reads the inverted Z of h) ...
 cudaError_t launch_verify_lad_b(const verify_args& a, cudaStream_t s);   // ... and its double-base ladder
 cudaError_t launch_verify_mul_a(const verify_args& a, cudaStream_t s);   // G*s - pk*c
 cudaError_t launch_verify_final(const verify_args& a, cudaStream_t s);
 cudaError_t launch_h2c_map(const h2c_args& a, cudaStream_t s);
 cudaError_t launch_h2c_out(const h2c_args& a, cudaStream_t s);
 cudaError_t launch_h2cw(int stage, const h2cw_args& a, cudaStream_t s);   // 0 map, 1 sum, 2 out
+cudaError_t launch_fbmul(int stage, const fbmul_args& a, cudaStream_t s);   // 0 map, 1 out
 cudaError_t launch_registers(uint32_t n, const uint8_t* in32, uint64_t* out4, cudaStream_t s);
 // batched inversion of m elements at Z (scratch same size), `per_thread` elements per thread
 cudaError_t launch_binv(uint32_t* Z, uint32_t* scratch, uint32_t m, uint32_t per_thread, cudaStream_t s);

@@ -11,14 +11,14 @@
 //   S2 affine R, pk; pk33; h = H2C(m || pk33) -> Jacobian               [sign_stage_h2c]
 //   BI batched inversion of Z_h
 //   S3 affine h; signed-comb table of h; h^r, h^sk -> Jacobian           [sign_stage_varbase_comb]
-//      (windowed ladder per scalar: sign_stage_varbase, -DPLUME_SIGN_WINDOWED / shared-memory table builds)
+//      (windowed ladder per scalar: sign_stage_varbase, -DPLUME_SIGN_WINDOWED builds)
 //   BI batched inversion of the 2 Z's
 //   S4 affine z, nul; c = SHA-256(...); s = r + c*sk; outputs + status   [sign_stage_final]
 // Verify (rust-k256/src/lib.rs:93-145):
 //   V1 input checks; h = H2C(m || enc(pk)) -> Jacobian                  [verify_stage_h2c]
 //   BI
 //   V2 window tables of h, nul [verify_stage_mul_b1]; B = s*h - c*nul [verify_stage_mul_b2]; A = s*G - c*pk
-//      [verify_stage_mul_a] -> Jacobian   (fused forms verify_stage_mul_b / verify_stage_muls behind build flags)
+//      [verify_stage_mul_a] -> Jacobian   (three kernels, each with its own register budget)
 //   BI
 //   V3 affine A, B; (V1: compare with r_point, hashed_to_curve_r); c == SHA-256(...) mod n  [verify_stage_final]
 #pragma once
@@ -285,7 +285,7 @@ struct sign_args {
     uint32_t* ws;
     const uint32_t* gtab;
     int gw;
-    uint32_t* vbtab;      // n x 128 words of table scratch (global-table builds only)
+    uint32_t* vbtab;      // n x COMB_AREA_WORDS words of table scratch
 };
 
 PLUME_DEV sc sc_one() { sc r; for (int i = 0; i < 8; i++) r.v[i] = (i == 0); return r; }
@@ -352,9 +352,8 @@ PLUME_DEV void sign_stage_h2c(uint32_t i, const sign_args& a) {
     ws_store_jac(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i, h);
 }
 
-// tab: this thread's table storage (vb_tab_strided in shared memory or vb_tab_linear in global scratch)
-template <class Tab>
-PLUME_DEV void sign_stage_varbase(uint32_t i, const sign_args& a, const Tab& tab) {
+// tab: VB_TAB_WORDS words of this thread's global scratch
+PLUME_DEV void sign_stage_varbase(uint32_t i, const sign_args& a, uint32_t* tab) {
     aff h = ws_load_affine(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i);
     ws_store_aff(a.ws, a.n, WS_HX, WS_HY, i, h);
     if (h.inf) {
@@ -365,7 +364,7 @@ PLUME_DEV void sign_stage_varbase(uint32_t i, const sign_args& a, const Tab& tab
         ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, o);
         return;
     }
-    fe zg = vb_build_table(h.x, h.y, tab);
+    fe zg = vb_build_table(h.x, h.y, tab, true);
     sc r = ld_sc_be(a.r + (size_t)i * 32);
     sc sk = ld_sc_be(a.sk + (size_t)i * 32);
     const bool zero_ok = a.flavour == PLUME_FLAVOUR_ARKWORKS;   // an Fr may be zero: h^0 is the identity
@@ -527,80 +526,18 @@ PLUME_DEV void verify_stage_h2c(uint32_t i, const verify_args& a) {
 }
 
 // k * P for an affine P that may be the identity
-template <class Tab>
-PLUME_DEV jac vb_mul_point(const aff& p, const sc& k, const Tab& tab) {
+PLUME_DEV jac vb_mul_point(const aff& p, const sc& k, uint32_t* tab) {
     if (p.inf) return jac_infinity();
-    fe zg = vb_build_table(p.x, p.y, tab);
+    fe zg = vb_build_table(p.x, p.y, tab, true);
     return vb_mul_tab(k, tab, zg);
 }
 
-// tab1, tab2: two table areas of this thread (global scratch)
-template <class Tab>
-PLUME_DEV void verify_stage_muls(uint32_t i, const verify_args& a, const Tab& tab1, const Tab& tab2) {
-    aff h = ws_load_affine(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i);
-    ws_store_aff(a.ws, a.n, WS_HX, WS_HY, i, h);
-    // remember whether h is the identity: WS_RX limb 0
-    st_fe(ws_at(a.ws, a.n, WS_RX, i), fe_set_u32(h.inf));
-    aff pk, nul;
-    bool good = a.ok[i] != 0;
-    sc c = sc_one(), s = sc_one();
-    if (good) {
-        ld_point_be(pk, a.pk + (size_t)i * 64);
-        ld_point_be(nul, a.nullifier + (size_t)i * 64);
-        c = ld_sc_be(a.c + (size_t)i * 32);
-        s = ld_sc_be(a.s + (size_t)i * 32);
-    } else {
-        pk = aff_generator();
-        nul = aff_generator();
-    }
-    sc mc = sc_neg(c);
-    // A = G*s - pk*c   (lib.rs:101): table walk for the generator, windowed ladder for pk
-    jac A = fb_mul(s, a.gtab, a.gw);
-    A = jac_add(A, vb_mul_point(pk, mc, tab1));
-    ws_store_jac(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i, A);
-    // B = h*s - nul*c  (lib.rs:109): one ladder over both tables (shared doublings)
-    jac B;
-    if (!h.inf && !nul.inf) {
-        fe zg = vb_build_table_pair(h.x, h.y, tab1, nul.x, nul.y, tab2);
-        B = vb_mul2_tab(s, tab1, mc, tab2, zg);
-    } else {
-        B = jac_add(vb_mul_point(h, s, tab1), vb_mul_point(nul, mc, tab1));
-    }
-    ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, B);
-}
-
-// The same work as two kernels (launched B first: it consumes the inverted Z of h in WS_Z0, which A's result then
-// overwrites).  Each half has its own register budget.
-template <class Tab>
-PLUME_DEV void verify_stage_mul_b(uint32_t i, const verify_args& a, const Tab& tab1, const Tab& tab2) {
-    aff h = ws_load_affine(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i);
-    ws_store_aff(a.ws, a.n, WS_HX, WS_HY, i, h);
-    st_fe(ws_at(a.ws, a.n, WS_RX, i), fe_set_u32(h.inf));
-    aff nul;
-    bool good = a.ok[i] != 0;
-    sc c = sc_one(), s = sc_one();
-    if (good) {
-        ld_point_be(nul, a.nullifier + (size_t)i * 64);
-        c = ld_sc_be(a.c + (size_t)i * 32);
-        s = ld_sc_be(a.s + (size_t)i * 32);
-    } else {
-        nul = aff_generator();
-    }
-    sc mc = sc_neg(c);
-    jac B;
-    if (!h.inf && !nul.inf) {
-        fe zg = vb_build_table_pair(h.x, h.y, tab1, nul.x, nul.y, tab2);
-        B = vb_mul2_tab(s, tab1, mc, tab2, zg);
-    } else {
-        B = jac_add(vb_mul_point(h, s, tab1), vb_mul_point(nul, mc, tab1));
-    }
-    ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, B);
-}
-// verify_stage_mul_b as two kernels: the table pair (b1) and the double-base ladder (b2), so that the ladder, which is
-// where the time goes, is compiled for 4 blocks per SM.  zg travels through WS_KX, the "ladder to do" flag through WS_RY;
+// h*s - nul*c as two kernels: the table pair (b1) and the double-base ladder (b2), so that the ladder, which is
+// where the time goes, is compiled for 4 blocks per SM (b1 runs first: it consumes the inverted Z of h in WS_Z0, which
+// the result of G*s - pk*c later overwrites).  tab1, tab2: two table areas of this thread (global scratch).
+// zg travels through WS_KX, the "ladder to do" flag through WS_RY;
 // the rare case of an identity among h, nul (adversarial inputs only) is finished inside b1.
-template <class Tab>
-PLUME_DEV void verify_stage_mul_b1(uint32_t i, const verify_args& a, const Tab& tab1, const Tab& tab2) {
+PLUME_DEV void verify_stage_mul_b1(uint32_t i, const verify_args& a, uint32_t* tab1, uint32_t* tab2) {
     aff h = ws_load_affine(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i);
     ws_store_aff(a.ws, a.n, WS_HX, WS_HY, i, h);
     st_fe(ws_at(a.ws, a.n, WS_RX, i), fe_set_u32(h.inf));
@@ -622,8 +559,7 @@ PLUME_DEV void verify_stage_mul_b1(uint32_t i, const verify_args& a, const Tab& 
     jac B = jac_add(vb_mul_point(h, s, tab1), vb_mul_point(nul, sc_neg(c), tab1));
     ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, B);
 }
-template <class Tab>
-PLUME_DEV void verify_stage_mul_b2(uint32_t i, const verify_args& a, const Tab& tab1, const Tab& tab2) {
+PLUME_DEV void verify_stage_mul_b2(uint32_t i, const verify_args& a, const uint32_t* tab1, const uint32_t* tab2) {
     if (ld_fe(ws_at(a.ws, a.n, WS_RY, i)).v[0] == 0) return;   // finished in b1
     sc c = sc_one(), s = sc_one();
     if (a.ok[i] != 0) {
@@ -633,8 +569,7 @@ PLUME_DEV void verify_stage_mul_b2(uint32_t i, const verify_args& a, const Tab& 
     jac B = vb_mul2_tab(s, tab1, sc_neg(c), tab2, ld_fe(ws_at(a.ws, a.n, WS_KX, i)));
     ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, B);
 }
-template <class Tab>
-PLUME_DEV void verify_stage_mul_a(uint32_t i, const verify_args& a, const Tab& tab1) {
+PLUME_DEV void verify_stage_mul_a(uint32_t i, const verify_args& a, uint32_t* tab1) {
     aff pk;
     bool good = a.ok[i] != 0;
     sc c = sc_one(), s = sc_one();
@@ -693,6 +628,25 @@ PLUME_DEV void h2c_stage_out(uint32_t i, const h2c_args& a) {
     st_point_be(a.out + (size_t)i * 64, h);
 }
 
+// ---- k * G for a batch of scalars (public keys from secret keys; the public-key field of the JS wire form's SEC1-DER
+// scalars, javascript/src/lib.rs:97-117) -------------------------------------------------------------------------------
+struct fbmul_args {
+    uint32_t n;
+    const uint8_t* k;         // n x 32 big-endian, taken mod n
+    uint8_t* out;             // n x 64 affine (zeros = identity)
+    uint32_t* ws;
+    const uint32_t* gtab;
+    int gw;
+};
+PLUME_DEV void fbmul_stage_map(uint32_t i, const fbmul_args& a) {
+    sc k = sc_reduce256(ld_sc_be(a.k + (size_t)i * 32));
+    ws_store_jac(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i, fb_mul(k, a.gtab, a.gw));
+}
+PLUME_DEV void fbmul_stage_out(uint32_t i, const fbmul_args& a) {
+    aff p = ws_load_affine(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i);
+    st_point_be(a.out + (size_t)i * 64, p);
+}
+
 // ---- hash_to_curve with its intermediates (what a circuit-input generator starts from) ----------------
 // The verify_nullifier circuit takes per-u witness hints (circuits/circom/verify_nullifier.circom:21-31) produced today by
 // the external generate_inputs_from_array (circuits/circom/test/v1.test.ts:5,38-40).  The device computes the RFC 9380
@@ -705,6 +659,7 @@ struct h2cw_args {
     uint8_t* q;          // n x 2 x 64  Q0, Q1 affine
     uint8_t* gx1_square; // n x 2       1 when g(x1) is a square (x = x1), 0 when x = x2 = Z u^2 x1
     uint8_t* h;          // n x 64      Q0 + Q1
+    uint8_t* hints;      // n x 2 x 3 x 32 or null: per u_k the circuit's gx1_sqrt, gx2_sqrt, y_pos (see h2cw_stage_map)
     uint32_t* ws;
 };
 PLUME_DEV void h2cw_stage_map(uint32_t i, const h2cw_args& a) {
@@ -716,9 +671,21 @@ PLUME_DEV void h2cw_stage_map(uint32_t i, const h2cw_args& a) {
     for (int k = 0; k < 2; k++) {
         fe u = fe_norm(k == 0 ? u0 : u1);
         st_fe_be(a.u + ((size_t)i * 2 + k) * 32, u);
-        fe xn, xd, y;
-        bool sq = h2c_map_sswu(xn, xd, y, u);
+        fe xn, xd, y, root;
+        bool sq = h2c_map_sswu(xn, xd, y, u, &root);
         a.gx1_square[(size_t)i * 2 + k] = sq ? 1 : 0;
+        if (a.hints) {
+            // Square-root hints of the circom hash_to_curve component (verify_nullifier.circom:21-31).  The generator that
+            // defines them is not in the reference tree, so the convention is DECLARED here: exactly one of g(x1), g(x2)
+            // is a square (Z is not); that one's hint is its EVEN square root (sgn0 = 0), the other hint is 0; y_pos is
+            // the even square root of g(x) for the x that was taken -- the map's y is y_pos or p - y_pos by sgn0(u).
+            root = fe_norm(root);
+            if (root.v[0] & 1) root = fe_norm(fe_neg(root));
+            uint8_t* hp = a.hints + ((size_t)i * 2 + k) * 96;
+            st_fe_be(hp, sq ? root : fe_zero());
+            st_fe_be(hp + 32, sq ? fe_zero() : root);
+            st_fe_be(hp + 64, root);
+        }
         jac qk = h2c_iso_map(xn, xd, y);
         if (k == 0) ws_store_jac(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i, qk);
         else ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, qk);

@@ -12,6 +12,9 @@ _lib = None
 SYMBOLS = {
     "plume_version": (ctypes.c_int, []),
     "plume_ctx_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int]),
+    "plume_ctx_create_multi": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int]),
+    "plume_ctx_device_count": (ctypes.c_int, [ctypes.c_void_p]),
+    "plume_ctx_sub": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_int]),
     "plume_ctx_destroy": (None, [ctypes.c_void_p]),
     "plume_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
     "plume_ctx_chunk_items": (ctypes.c_size_t, [ctypes.c_void_p]),
@@ -21,7 +24,10 @@ SYMBOLS = {
                                           _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p]),
     "plume_hash_to_curve_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, _u8p, _u8p, ctypes.c_size_t, _u8p]),
     "plume_hash_to_curve_witness_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, _u8p, _u8p, ctypes.c_size_t,
-                                                         _u8p, _u8p, _u8p, _u8p]),
+                                                         _u8p, _u8p, _u8p, _u8p, _u8p]),
+    "plume_fixed_base_mul_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, _u8p, _u8p]),
+    "plume_debug_read_arena": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u8p, _u8p, ctypes.c_size_t,
+                                              ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]),
     "plume_registers_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, _u8p, _u8p]),
     "plume_ark_sign_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, _u8p, _u8p, ctypes.c_size_t,
                                             _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p]),

@@ -54,21 +54,46 @@ def pack_messages(msgs):
 
 
 class PlumeContext:
-    """One GPU's signer/verifier (plume_ctx_create).  One context per process per GPU."""
+    """A signer/verifier context: one GPU (plume_ctx_create) or, when `device` is a list of ordinals, several GPUs of
+    this process behind one context (plume_ctx_create_multi: the host-pointer batch calls range-split over them)."""
 
-    def __init__(self, device=0, fixed_window_bits=0):
+    def __init__(self, device=0, fixed_window_bits=0, _handle=None):
         self._lib = _lib.load()
+        self._owned = _handle is None
+        if _handle is not None:
+            self._h = ctypes.c_void_p(_handle)
+            self.device = device
+            return
         h = ctypes.c_void_p()
-        rc = self._lib.plume_ctx_create(ctypes.byref(h), int(device), int(fixed_window_bits))
+        if isinstance(device, (list, tuple)):
+            devs = (ctypes.c_int * len(device))(*[int(d) for d in device])
+            rc = self._lib.plume_ctx_create_multi(ctypes.byref(h), devs, len(device), int(fixed_window_bits))
+            what = "plume_ctx_create_multi"
+        else:
+            rc = self._lib.plume_ctx_create(ctypes.byref(h), int(device), int(fixed_window_bits))
+            what = "plume_ctx_create"
         if rc != 0:
-            raise PlumeError("plume_ctx_create failed (%d): %s" % (rc, self._lib.plume_last_error(None).decode()))
+            raise PlumeError("%s failed (%d): %s" % (what, rc, self._lib.plume_last_error(None).decode()))
         self._h = h
         self.device = device
 
     def close(self):
         if getattr(self, "_h", None):
-            self._lib.plume_ctx_destroy(self._h)
+            if self._owned:
+                self._lib.plume_ctx_destroy(self._h)
             self._h = None
+
+    @property
+    def device_count(self):
+        return self._lib.plume_ctx_device_count(self._h)
+
+    def sub(self, i):
+        """The i-th per-device context of a multi-device context (borrowed: closing it is a no-op)."""
+        h = self._lib.plume_ctx_sub(self._h, int(i))
+        if not h:
+            raise PlumeError("no sub-context %d" % i)
+        dev = self.device[i] if isinstance(self.device, (list, tuple)) else self.device
+        return PlumeContext(dev, _handle=h)
 
     def __del__(self):
         try:
@@ -169,9 +194,10 @@ class PlumeContext:
         """plume_hash_to_curve_witness_batch: dict u [n,2,32], q [n,2,64], gx1_square [n,2], h [n,64]."""
         blob, offs, mlen, n = self._msgs(msgs, None)
         o = {"u": np.empty((n, 2, 32), dtype=np.uint8), "q": np.empty((n, 2, 64), dtype=np.uint8),
-             "gx1_square": np.empty((n, 2), dtype=np.uint8), "h": np.empty((n, 64), dtype=np.uint8)}
+             "gx1_square": np.empty((n, 2), dtype=np.uint8), "h": np.empty((n, 64), dtype=np.uint8),
+             "hints": np.empty((n, 2, 3, 32), dtype=np.uint8)}   # per u: gx1_sqrt, gx2_sqrt, y_pos (declared convention)
         rc = self._lib.plume_hash_to_curve_witness_batch(self._h, n, _ptr(blob), _ptr(offs), mlen, _ptr(o["u"]), _ptr(o["q"]),
-                                                         _ptr(o["gx1_square"]), _ptr(o["h"]))
+                                                         _ptr(o["gx1_square"]), _ptr(o["h"]), _ptr(o["hints"]))
         self._check(rc, "plume_hash_to_curve_witness_batch")
         return o
 
@@ -182,6 +208,23 @@ class PlumeContext:
         out = np.empty((n, 4), dtype=np.uint64)
         self._check(self._lib.plume_registers_batch(self._h, n, _ptr(a), _ptr(out)), "plume_registers_batch")
         return out.reshape(a.shape[:-1] + (4,)) if a.ndim > 1 else out
+
+    def fixed_base_mul_batch(self, scalars32):
+        """plume_fixed_base_mul_batch: u8[n,32] big-endian scalars -> u8[n,64] points k*G."""
+        a = _as_u8(scalars32)
+        n = a.size // 32
+        a = a.reshape(n, 32)
+        out = np.empty((n, 64), dtype=np.uint8)
+        self._check(self._lib.plume_fixed_base_mul_batch(self._h, n, _ptr(a), _ptr(out)), "plume_fixed_base_mul_batch")
+        return out
+
+    def debug_read_arena(self, lane, cap=1 << 26):
+        """(device arena bytes, pinned staging bytes) of lane 0/1 after the streams drained -- test hook."""
+        d = np.zeros(cap, dtype=np.uint8); h = np.zeros(cap, dtype=np.uint8)
+        nd, nh = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        self._check(self._lib.plume_debug_read_arena(self._h, lane, _ptr(d), _ptr(h), cap, ctypes.byref(nd), ctypes.byref(nh)),
+                    "plume_debug_read_arena")
+        return d[:nd.value], h[:nh.value]
 
     # ---- arkworks flavour (rust-arkworks/src/lib.rs:229-278, tests.rs:28-78) -----------------------------
     def ark_sign_batch(self, version, msgs, pk, sk, r):
@@ -342,6 +385,80 @@ def encode_pt(p):
     return b"\x00" if p is None else bytes([2 + (p[1] & 1)]) + p[0].to_bytes(32, "big")
 
 
+# ---- SEC1-DER scalars: the JS wire form of c and s (javascript/src/lib.rs:97-117) -------------------------------------
+# `SecretKey::from(scalar).to_sec1_der()` of elliptic-curve 0.13 / sec1 0.7 (external crates, not in the reference tree;
+# no reference test pins the bytes): ECPrivateKey ::= SEQUENCE { version INTEGER 1, privateKey OCTET STRING (32),
+# publicKey [1] BIT STRING (uncompressed k*G) } with the curve parameters omitted:
+#     30 6b  02 01 01  04 20 <k: 32 bytes>  a1 44 03 42 00  04 <x: 32> <y: 32>            (109 bytes)
+_DER_HEAD = bytes.fromhex("306b0201010420")
+_DER_MID = bytes.fromhex("a14403420004")
+
+
+def scalars_to_sec1_der(scalars32, ctx=None):
+    """u8[n,32] big-endian scalars in [1, n-1] -> list of 109-byte SEC1-DER EC private keys (public keys k*G from the GPU)."""
+    a = _as_u8(scalars32)
+    n = a.size // 32
+    a = a.reshape(n, 32)
+    for row in a:
+        if not (1 <= int.from_bytes(bytes(row), "big") < ORDER):
+            raise ValueError("scalar outside [1, n-1] has no SecretKey form")
+    pub = (ctx or default_context()).fixed_base_mul_batch(a)
+    return [_DER_HEAD + bytes(a[i]) + _DER_MID + bytes(pub[i]) for i in range(n)]
+
+
+def scalar_from_sec1_der(der, ctx=None, check_public_key=True):
+    """`SecretKey::from_sec1_der`: accepts the form above, and the same without the optional public key or with the
+    optional secp256k1 parameters ([0] OID 1.3.132.0.10); when a public key is present it must equal k*G (k256 rejects a
+    mismatch).  Returns the scalar as an int; raises ValueError on anything else."""
+    der = bytes(der)
+
+    def tlv(buf, pos):
+        if pos + 2 > len(buf):
+            raise ValueError("truncated DER")
+        tag, ln = buf[pos], buf[pos + 1]
+        pos += 2
+        if ln & 0x80:
+            k = ln & 0x7F
+            if k == 0 or k > 2 or pos + k > len(buf):
+                raise ValueError("bad DER length")
+            ln = int.from_bytes(buf[pos:pos + k], "big")
+            pos += k
+        if pos + ln > len(buf):
+            raise ValueError("truncated DER")
+        return tag, buf[pos:pos + ln], pos + ln
+
+    tag, body, end = tlv(der, 0)
+    if tag != 0x30 or end != len(der):
+        raise ValueError("not a DER SEQUENCE")
+    tag, ver, pos = tlv(body, 0)
+    if tag != 0x02 or ver != b"\x01":
+        raise ValueError("ECPrivateKey version must be 1")
+    tag, key, pos = tlv(body, pos)
+    if tag != 0x04 or len(key) != 32:
+        raise ValueError("privateKey must be a 32-byte OCTET STRING")
+    k = int.from_bytes(key, "big")
+    if not (1 <= k < ORDER):
+        raise ValueError("scalar outside [1, n-1]")
+    pub = None
+    while pos < len(body):
+        tag, val, pos = tlv(body, pos)
+        if tag == 0xA0:
+            if val != bytes.fromhex("06052b8104000a"):
+                raise ValueError("parameters are not secp256k1")
+        elif tag == 0xA1:
+            t2, bits, e2 = tlv(val, 0)
+            if t2 != 0x03 or e2 != len(val) or len(bits) != 66 or bits[0] != 0 or bits[1] != 4:
+                raise ValueError("publicKey must be an uncompressed point")
+            pub = bits[2:]
+        else:
+            raise ValueError("unexpected field in ECPrivateKey")
+    if pub is not None and check_public_key:
+        want = (ctx or default_context()).fixed_base_mul_batch(np.frombuffer(key, dtype=np.uint8))
+        if bytes(want[0]) != pub:
+            raise ValueError("public key does not match the private key")
+    return k
+
+
 # ---- the reference's types ----------------------------------------------------------------------------------
 class PlumeSignatureV1Fields:
     """rust-k256/src/lib.rs:84-89"""
@@ -424,6 +541,53 @@ class PlumeSignature:
                               point_to_bytes(v1.r_point) if v1 else None,
                               point_to_bytes(v1.hashed_to_curve_r) if v1 else None)
         return bool(ok[0])
+
+    # ---- wire form: the serde derive of rust-k256/src/lib.rs:66,83 through serde_json ---------------------------------
+    # The struct derives Serialize/Deserialize behind the default feature `serde` (Cargo.toml:26-28 turns on k256/serde).
+    # The field encodings come from k256 0.13 / elliptic-curve 0.13 (external crates; NO reference test pins them -- SURVEY.md
+    # 8c "parity unpinned"): in a human-readable format AffinePoint is the upper-case hex of its SEC1 *compressed* encoding
+    # and NonZeroScalar the upper-case hex of its 32 big-endian bytes (serdect), `message: Vec<u8>` is an array of numbers,
+    # `v1specific` is an object or null.  Field order is the declaration order.
+    def to_json(self):
+        import json
+        hexu = lambda b: bytes(b).hex().upper()
+        d = {"message": list(self.message), "pk": hexu(encode_pt(self.pk)), "nullifier": hexu(encode_pt(self.nullifier)),
+             "c": hexu(self.c.to_bytes(32, "big")), "s": hexu(self.s.to_bytes(32, "big")), "v1specific": None}
+        if self.v1specific is not None:
+            d["v1specific"] = {"r_point": hexu(encode_pt(self.v1specific.r_point)),
+                               "hashed_to_curve_r": hexu(encode_pt(self.v1specific.hashed_to_curve_r))}
+        return json.dumps(d, separators=(",", ":"))
+
+    @classmethod
+    def from_json(cls, text, ctx=None):
+        """Inverse of to_json.  Points are decompressed on the GPU (plume_points_decompress_batch); a point that k256's
+        AffinePoint decoding would reject, or a scalar outside [1, n-1] (NonZeroScalar), raises ValueError."""
+        import json
+        d = json.loads(text)
+        ctx = ctx or default_context()
+        names = ["pk", "nullifier"]
+        enc = [bytes.fromhex(d["pk"]), bytes.fromhex(d["nullifier"])]
+        v1 = d.get("v1specific")
+        if v1 is not None:
+            names += ["r_point", "hashed_to_curve_r"]
+            enc += [bytes.fromhex(v1["r_point"]), bytes.fromhex(v1["hashed_to_curve_r"])]
+        slots = np.zeros((len(enc), 33), dtype=np.uint8)
+        for i, e in enumerate(enc):
+            if not (len(e) == 33 or e == b"\x00"):
+                raise ValueError("%s is not a SEC1 compressed point" % names[i])
+            slots[i, :len(e)] = np.frombuffer(e, dtype=np.uint8)
+        pts, ok = ctx.points_decompress(slots)
+        if not ok.all():
+            raise ValueError("%s does not decode to a curve point" % names[int(np.argmin(ok))])
+        sc = {}
+        for k in ("c", "s"):
+            b = bytes.fromhex(d[k])
+            if len(b) != 32 or not (1 <= int.from_bytes(b, "big") < ORDER):
+                raise ValueError("%s is not a NonZeroScalar" % k)
+            sc[k] = int.from_bytes(b, "big")
+        p = [point_from_bytes(x) for x in pts]
+        v1f = PlumeSignatureV1Fields(p[2], p[3]) if v1 is not None else None
+        return cls(bytes(d["message"]), p[0], p[1], sc["c"], sc["s"], v1f, ctx=ctx)
 
     @staticmethod
     def sign_v1(secret_key, msg, rng, ctx=None):

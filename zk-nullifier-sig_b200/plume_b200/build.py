@@ -16,9 +16,8 @@ if PKG not in sys.path:
 CSRC = os.path.join(PKG, "csrc")
 BUILD = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libplume_b200.so")
-UNITS = ["api", "k_sign", "k_verify", "k_misc"]
+UNITS = ["api", "api_multi", "k_sign", "k_verify", "k_misc"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-SASS_PATCH_DEFAULT = False
 NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-no-compress"]
 
 
@@ -42,16 +41,13 @@ def _stale(target, sources):
     return any(os.path.getmtime(s) > t for s in sources)
 
 
-def build(force=False, verbose=True, variant=None, defines=(), sass_patch=None):
+def build(force=False, verbose=True, variant=None, defines=()):
     """variant/defines: build an experiment library libplume_b200_<variant>.so with extra -D flags
     (selected at run time with PLUME_B200_LIB=<path>); the default build is the shipped library."""
     global BUILD, LIB
     if variant:
         BUILD = os.path.join(PKG, "build", variant)
         LIB = os.path.join(PKG, "libplume_b200_%s.so" % variant)
-    if sass_patch is None:
-        sass_patch = SASS_PATCH_DEFAULT and "NOSASSPATCH" not in defines
-    defines = [d for d in defines if d != "NOSASSPATCH"]
     os.makedirs(BUILD, exist_ok=True)
     nvcc = _nvcc()
     deps = _deps()
@@ -66,17 +62,13 @@ def build(force=False, verbose=True, variant=None, defines=(), sass_patch=None):
             r = subprocess.run([nvcc] + flags + ["-c", src, "-o", obj], stdout=lf, stderr=subprocess.STDOUT)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s" % (u, open(log).read()[-4000:]))
-        if sass_patch:   # register moves off the FMA-heavy pipe (sasspatch.py)
-            from plume_b200 import sasspatch
-            with open(log, "a") as lf:
-                lf.write("sasspatch: %d of %d IMAD.MOV.U32 -> MOV\n" % sasspatch.patch_file(obj))
         return u, True
 
     with ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
         results = list(ex.map(compile_unit, UNITS))
     objs = [os.path.join(BUILD, u + ".o") for u in UNITS]
     if force or any(ch for _, ch in results) or _stale(LIB, objs):
-        r = subprocess.run([nvcc] + ARCH + ["-shared", "-cudart", "static", "-o", LIB] + objs,
+        r = subprocess.run([nvcc] + ARCH + ["-shared", "-cudart", "static", "-o", LIB] + objs + ["-ldl", "-lpthread"],
                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout)
@@ -87,8 +79,7 @@ def build(force=False, verbose=True, variant=None, defines=(), sass_patch=None):
 
 if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
-    if args:   # build.py <variant> DEF1 DEF2=val ... [SASSPATCH | NOSASSPATCH]
-        build(force="--force" in sys.argv, variant=args[0], defines=[a for a in args[1:] if a != "SASSPATCH"],
-              sass_patch=True if "SASSPATCH" in args else None)
+    if args:   # build.py <variant> DEF1 DEF2=val ...
+        build(force="--force" in sys.argv, variant=args[0], defines=args[1:])
     else:
         build(force="--force" in sys.argv)
