@@ -90,6 +90,8 @@ void plume_ctx_destroy(plume_ctx* ctx);
  * NVLink / ncclBroadcast; measured, not faster: DESIGN.md section 6). */
 int plume_ctx_create_multi(plume_ctx** out, const int* devices, int n_devices, int fixed_window_bits);
 int plume_ctx_device_count(const plume_ctx* ctx);          /* 1 for a single-device context */
+/* The range split itself (no device needed): part `part` of `parts` owns items [first, first + count) of n. */
+int plume_shard_range(size_t n, int part, int parts, size_t* first, size_t* count);
 plume_ctx* plume_ctx_sub(plume_ctx* ctx, int i);           /* the i-th per-device context (ctx itself when single) */
 
 /* Last error text of this context (or of context creation when ctx is NULL). */

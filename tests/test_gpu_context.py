@@ -1,0 +1,240 @@
+"""Context-level behaviour of the C ABI on the GPU (round 2): the multi-device context (one caller, one host batch, G GPUs),
+the stream-ordering contract between `_device` and host-pointer calls, clean error exits, wiping of the library's copies
+of secret keys and nonces, and the wire helpers (k*G batch, SEC1-DER scalars, the serde-JSON form of PlumeSignature).
+Every result is compared with the C oracle on the same inputs."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+N = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+FIELDS = ("status", "pk", "nullifier", "c", "s", "r_point", "hashed_to_curve_r")
+
+
+def _scalars(rng, n):
+    a = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    a[:, 0] &= 0x7F
+    return a
+
+
+def _device_list():
+    import torch
+    n = torch.cuda.device_count()
+    return list(range(min(n, 8)))
+
+
+def test_multi_device_context_bit_exact():
+    """plume_ctx_create_multi: the host-pointer calls range-split over every visible GPU (one worker thread each) and write
+    into the caller's arrays; identical to the oracle.  On a one-GPU box this still runs the multi-device code path with a
+    single sub-context."""
+    import c_oracle
+    import plume_b200
+    devs = _device_list()
+    threads = os.cpu_count() or 1
+    rnd = random.Random(77)
+    rng = np.random.default_rng(77)
+    with plume_b200.PlumeContext(devs) as ctx:
+        assert ctx.device_count == len(devs)
+        # ragged messages, a size that does not divide by the device count, both versions
+        n = 3001
+        msgs = [bytes(rnd.randrange(256) for _ in range(rnd.choice([0, 1, 29, 32, 33, 65, 100]))) for _ in range(n)]
+        sk, r = _scalars(rng, n), _scalars(rng, n)
+        sk[5] = 0   # a rejected item in the first shard
+        for ver in (1, 2):
+            got = ctx.sign_batch(ver, msgs, sk, r)
+            want = c_oracle.sign_batch(ver, msgs, sk, r, threads=threads)
+            for k in FIELDS:
+                assert np.array_equal(got[k], want[k]), (ver, k)
+            ok = ctx.verify_batch(ver, msgs, got["pk"], got["nullifier"], got["c"], got["s"], got["r_point"], got["hashed_to_curve_r"])
+            want_ok = c_oracle.verify_batch(ver, msgs, got["pk"], got["nullifier"], got["c"], got["s"], got["r_point"],
+                                            got["hashed_to_curve_r"], threads=threads)
+            assert np.array_equal(ok, want_ok) and ok.sum() == n - 1
+        # fixed-length records at a size that spans several chunks per device
+        n = 1 << 16
+        fixed = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        sk, r = _scalars(rng, n), _scalars(rng, n)
+        got = ctx.sign_batch(1, fixed, sk, r)
+        want = c_oracle.sign_batch(1, fixed, sk, r, threads=threads)
+        for k in FIELDS:
+            assert np.array_equal(got[k], want[k]), k
+        pre = rng.integers(0, 256, (4099, 65), dtype=np.uint8)
+        assert np.array_equal(ctx.hash_to_curve_batch(pre), c_oracle.h2c_batch(pre, threads=threads))
+        c33 = ctx.points_compress(got["pk"][:1000])
+        back, okf = ctx.points_decompress(c33)
+        assert okf.all() and np.array_equal(back, got["pk"][:1000])
+        # device-pointer entry points belong to the per-device contexts
+        with pytest.raises(plume_b200.PlumeError):
+            ctx.hash_to_curve_batch_device(1, 0, 0, 65, 0)
+        sub = ctx.sub(len(devs) - 1)
+        assert np.array_equal(sub.hash_to_curve_batch(pre[:64]), c_oracle.h2c_batch(pre[:64]))
+        assert ctx.launch_count > 0
+
+
+def test_multi_device_two_gpus_disjoint_work():
+    """With two or more GPUs: every device really processes its own range (per-device launch counters move)."""
+    import plume_b200
+    devs = _device_list()
+    if len(devs) < 2:
+        pytest.skip("one GPU visible")
+    rng = np.random.default_rng(5)
+    with plume_b200.PlumeContext(devs[:2]) as ctx:
+        before = [ctx.sub(i).launch_count for i in range(2)]
+        n = 4096
+        ctx.sign_batch(2, rng.integers(0, 256, (n, 32), dtype=np.uint8), _scalars(rng, n), _scalars(rng, n))
+        after = [ctx.sub(i).launch_count for i in range(2)]
+        assert all(a > b for a, b in zip(after, before))
+
+
+def test_device_and_host_calls_interleaved_without_sync(gpu_ctx):
+    """A `_device` call in flight on a caller stream followed at once by a host-pointer call (round 1 shared one workspace
+    between the two and raced): both must be bit-exact.  Also two `_device` calls on different streams back to back."""
+    import torch
+    import c_oracle
+    threads = os.cpu_count() or 1
+    rng = np.random.default_rng(11)
+    n = 1 << 15
+    dev = torch.device("cuda", 0)
+    ins = []
+    for _ in range(3):
+        ins.append((rng.integers(0, 256, (n, 32), dtype=np.uint8), _scalars(rng, n), _scalars(rng, n)))
+    want = [c_oracle.sign_batch(1, m, sk, r, threads=threads) for m, sk, r in ins]
+    outs = []
+    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    D = []
+    for q in range(2):
+        m, sk, r = ins[q]
+        d = {"m": torch.from_numpy(m).to(dev), "sk": torch.from_numpy(sk).to(dev), "r": torch.from_numpy(r).to(dev)}
+        for k, w in (("pk", 64), ("nullifier", 64), ("c", 32), ("s", 32), ("r_point", 64), ("hashed_to_curve_r", 64)):
+            d[k] = torch.empty((n, w), dtype=torch.uint8, device=dev)
+        d["status"] = torch.empty(n, dtype=torch.uint8, device=dev)
+        D.append(d)
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for q in range(2):   # two device calls on two different streams, no sync in between
+            d = D[q]
+            gpu_ctx.sign_batch_device(1, n, d["m"].data_ptr(), 0, 32, d["sk"].data_ptr(), d["r"].data_ptr(), d["pk"].data_ptr(),
+                                      d["nullifier"].data_ptr(), d["c"].data_ptr(), d["s"].data_ptr(), d["r_point"].data_ptr(),
+                                      d["hashed_to_curve_r"].data_ptr(), d["status"].data_ptr(), streams[q].cuda_stream)
+        m, sk, r = ins[2]
+        outs = gpu_ctx.sign_batch(1, m, sk, r)   # host-pointer call while the device calls are still running
+        torch.cuda.synchronize()
+        for k in FIELDS:
+            assert np.array_equal(outs[k], want[2][k]), ("host", rep, k)
+            for q in range(2):
+                assert np.array_equal(D[q][k].cpu().numpy(), want[q][k]), ("device", q, rep, k)
+
+
+def test_secrets_are_wiped_from_library_memory():
+    """After a signing call the library's own copies of sk and r (device arena, pinned staging arena) hold zeros."""
+    import plume_b200
+    rng = np.random.default_rng(3)
+    n = 5000
+    with plume_b200.PlumeContext(0) as ctx:
+        msgs = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        sk, r = _scalars(rng, n), _scalars(rng, n)
+        sk[:, 8:16] = np.frombuffer(b"SECRETSK", dtype=np.uint8)      # recognisable markers inside every secret
+        r[:, 8:16] = np.frombuffer(b"NONCE--R", dtype=np.uint8)
+        out = ctx.sign_batch(1, msgs, sk, r)                           # pageable numpy memory: staged through the pinned arena
+        assert (out["status"] == 0).all()
+        seen_any = False
+        for lane in (0, 1):
+            d, h = ctx.debug_read_arena(lane)
+            for buf in (d, h):
+                if buf.size:
+                    seen_any = True
+                    b = buf.tobytes()
+                    assert b"SECRETSK" not in b and b"NONCE--R" not in b
+        assert seen_any
+        # the outputs (public) are of course still there to be read by the caller
+        assert out["pk"].any()
+
+
+def test_bad_offsets_and_failed_allocation_leave_the_context_usable():
+    import c_oracle
+    import plume_b200
+    rng = np.random.default_rng(4)
+    with plume_b200.PlumeContext(0) as ctx:
+        n = 64
+        blob = rng.integers(0, 256, 64 * 10, dtype=np.uint8)
+        offs = np.arange(0, 10 * (n + 1), 10, dtype=np.uint64)
+        bad = offs.copy(); bad[7] = bad[9] + 1          # decreasing
+        sk, r = _scalars(rng, n), _scalars(rng, n)
+        with pytest.raises(plume_b200.PlumeError) as e:
+            ctx.sign_batch(1, (blob, bad), sk, r)
+        assert "(-1)" in str(e.value) and "non-decreasing" in str(e.value)
+        # an allocation that cannot succeed: PLUME_E_NOMEM, nothing left in flight, the next call works
+        huge = np.zeros((1, 1), dtype=np.uint8)
+        out = np.empty((300000, 64), dtype=np.uint8)
+        rc = ctx._lib.plume_hash_to_curve_batch(ctx._h, 300000, huge.ctypes.data, None, 0xFFFFFFF0, out.ctypes.data)
+        assert rc == -4, rc
+        good = ctx.sign_batch(1, (blob, offs), sk, r)
+        want = c_oracle.sign_batch(1, [bytes(blob[10 * i:10 * i + 10]) for i in range(n)], sk, r)
+        for k in FIELDS:
+            assert np.array_equal(good[k], want[k]), k
+
+
+def test_fixed_base_mul_and_sec1_der_scalars(gpu_ctx):
+    """k*G batch against the oracle, and the JS wire form's SEC1-DER scalars (javascript/src/lib.rs:97-117): structure,
+    round trip, public-key check."""
+    import c_oracle
+    import plume_b200
+    rnd = random.Random(9)
+    ks = [1, 2, N - 1, N - 2, 2**128, 2**255] + [rnd.randrange(1, N) for _ in range(300)]
+    arr = np.frombuffer(b"".join(k.to_bytes(32, "big") for k in ks), dtype=np.uint8).reshape(len(ks), 32)
+    pts = gpu_ctx.fixed_base_mul_batch(arr)
+    for i, k in enumerate(ks):
+        assert bytes(pts[i]) == c_oracle.mul_g(k), hex(k)
+    # 0 and n give the identity, n + 5 is taken mod n
+    edge = np.frombuffer(b"".join(v.to_bytes(32, "big") for v in (0, N, N + 5)), dtype=np.uint8).reshape(3, 32)
+    e = gpu_ctx.fixed_base_mul_batch(edge)
+    assert bytes(e[0]) == bytes(64) and bytes(e[1]) == bytes(64) and bytes(e[2]) == c_oracle.mul_g(5)
+    ders = plume_b200.scalars_to_sec1_der(arr[:40], ctx=gpu_ctx)
+    for i, der in enumerate(ders):
+        assert len(der) == 109 and der[:7] == bytes.fromhex("306b0201010420") and der[39:45] == bytes.fromhex("a14403420004")
+        assert der[7:39] == bytes(arr[i]) and der[45:] == bytes(pts[i])
+        assert plume_b200.scalar_from_sec1_der(der, ctx=gpu_ctx) == ks[i]
+        assert plume_b200.scalar_from_sec1_der(der[:2].replace(b"\x6b", b"\x25") + der[2:39], ctx=gpu_ctx) == ks[i]   # no public key
+    bad = bytearray(ders[7]); bad[60] ^= 1
+    with pytest.raises(ValueError):
+        plume_b200.scalar_from_sec1_der(bytes(bad), ctx=gpu_ctx)
+    with pytest.raises(ValueError):
+        plume_b200.scalars_to_sec1_der(edge[:1], ctx=gpu_ctx)
+
+
+def test_serde_json_wire_form_round_trip(gpu_ctx, golden):
+    """PlumeSignature <-> the serde_json form of the derive at rust-k256/src/lib.rs:66,83 (field encodings per k256 0.13:
+    upper-case hex of compressed points / 32-byte scalars; unpinned by the reference -- this pins OUR reader and writer to
+    each other and to the reference's KAT values)."""
+    import plume_b200
+    k = golden["sign_kat"]
+
+    class Mock:
+        def fill_bytes(self, buf):
+            buf[:] = bytes.fromhex(k["r"]["hex"])
+
+    sk = plume_b200.SecretKey.from_bytes(bytes.fromhex(k["sk"]["hex"]))
+    for v1 in (True, False):
+        sig = (plume_b200.PlumeSignature.sign_v1 if v1 else plume_b200.PlumeSignature.sign_v2)(sk, k["message_ascii"].encode(), Mock(), ctx=gpu_ctx)
+        text = sig.to_json()
+        d = json.loads(text)
+        assert list(d) == ["message", "pk", "nullifier", "c", "s", "v1specific"]
+        assert bytes(d["message"]) == k["message_ascii"].encode()
+        assert d["c"] == k["v1_c" if v1 else "v2_c"]["hex"].upper() and d["s"] == k["v1_s" if v1 else "v2_s"]["hex"].upper()
+        inter = golden["intermediates"]
+        assert d["pk"][2:] == inter["pk"]["x"].upper() and d["pk"][:2] in ("02", "03")
+        assert d["nullifier"][2:] == inter["h_sk"]["x"].upper()
+        assert (d["v1specific"] is not None) == v1
+        back = plume_b200.PlumeSignature.from_json(text, ctx=gpu_ctx)
+        assert (back.pk, back.nullifier, back.c, back.s) == (sig.pk, sig.nullifier, sig.c, sig.s)
+        assert back.verify()
+        if v1:
+            assert back.v1specific.r_point == sig.v1specific.r_point
+        tampered = json.loads(text); tampered["nullifier"] = tampered["pk"]
+        assert not plume_b200.PlumeSignature.from_json(json.dumps(tampered), ctx=gpu_ctx).verify()
+        broken = json.loads(text); broken["c"] = "00" * 32
+        with pytest.raises(ValueError):
+            plume_b200.PlumeSignature.from_json(json.dumps(broken), ctx=gpu_ctx)

@@ -62,6 +62,27 @@ def test_range_split_unit():
         plume_b200.shard_range(10, 2, 2)
 
 
+def test_library_range_split_matches():
+    """The split the multi-device context applies inside libplume_b200.so (plume_shard_range, no GPU needed) is the same
+    rule: it tiles the batch in order for any device count, including batches smaller than the device count."""
+    import ctypes
+    import plume_b200
+    lib = plume_b200.load()
+    for n in (0, 1, 5, 7, 8, 1000, (1 << 20) + 1, (1 << 24) + 3, (1 << 63) + 12345):
+        for parts in (1, 2, 3, 5, 8, 16):
+            pos = 0
+            for g in range(parts):
+                f, c = ctypes.c_size_t(0), ctypes.c_size_t(0)
+                assert lib.plume_shard_range(n, g, parts, ctypes.byref(f), ctypes.byref(c)) == 0
+                assert f.value == pos
+                if n < (1 << 60):
+                    assert (f.value, f.value + c.value) == plume_b200.shard_range(n, g, parts)
+                pos += c.value
+            assert pos == n
+    f, c = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    assert lib.plume_shard_range(10, 2, 2, ctypes.byref(f), ctypes.byref(c)) == -1
+
+
 def test_two_ranks_gloo(tmp_path):
     import torch.multiprocessing as mp
     import bench

@@ -382,7 +382,7 @@ int ctx_create_single(plume_ctx** out, int device, int fixed_window_bits, const 
     c->host_chunk = env_size("PLUME_HOST_CHUNK_ITEMS", (size_t)prop.multiProcessorCount * 128 * 12);
     if (c->host_chunk > c->chunk) c->host_chunk = c->chunk;
     c->binv_k = (uint32_t)env_size("PLUME_BINV_K", 16);
-    c->stage_threads = (int)env_size("PLUME_STAGE_THREADS", 4);
+    c->stage_threads = (int)env_size("PLUME_STAGE_THREADS", 8);
     struct Guard { plume_ctx* c; ~Guard() { if (c) plume_ctx_destroy(c); } } guard{c};
     for (int k = 0; k < 2; k++) CU(cudaStreamCreateWithFlags(&c->lanes[k].stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->dev_done, cudaEventDisableTiming));

@@ -61,10 +61,26 @@ struct Worker {
     }
 };
 
+// the range split of SURVEY.md 8e: part g of G owns items [g n / G, (g+1) n / G) -- sizes differ by at most one and the
+// parts tile [0, n) in order.  Exported so that the rule can be checked without a GPU (tests/test_sharding_gloo.py) and
+// reused by callers that shard across processes (bench.py's torchrun ranks use the same formula).
+extern "C" int plume_shard_range(size_t n, int part, int parts, size_t* first, size_t* count) {
+    if (parts < 1 || part < 0 || part >= parts || !first || !count) return PLUME_E_ARG;
+    // n * part can exceed 64 bits only for n > 2^64 / parts; split the product to stay exact for any size_t n
+    const size_t q = n / (size_t)parts, r = n % (size_t)parts;
+    const size_t lo = q * (size_t)part + (r * (size_t)part) / (size_t)parts;
+    const size_t hi = q * (size_t)(part + 1) + (r * (size_t)(part + 1)) / (size_t)parts;
+    *first = lo;
+    *count = hi - lo;
+    return PLUME_OK;
+}
+
 int multi_split(plume_ctx* ctx, size_t n, const std::function<int(plume_ctx*, size_t, size_t)>& f) {
     const size_t G = ctx->subs.size();
     for (size_t g = 0; g < G; g++) {
-        const size_t first = n * g / G, last = n * (g + 1) / G;
+        size_t first = 0, count = 0;
+        plume_shard_range(n, (int)g, (int)G, &first, &count);
+        const size_t last = first + count;
         plume_ctx* sub = ctx->subs[g];
         ctx->workers[g]->post([&f, sub, first, last]() -> int { return last > first ? f(sub, first, last - first) : PLUME_OK; });
     }

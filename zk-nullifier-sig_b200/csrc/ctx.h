@@ -43,7 +43,7 @@ struct plume_ctx {
     size_t chunk = 0;        // largest n of one pass (what the `_device` entry points accept)
     size_t host_chunk = 0;   // pipelining granularity of the host-pointer entry points
     uint32_t binv_k = 16;
-    int stage_threads = 4;   // threads of a staging memcpy (pageable callers)
+    int stage_threads = 8;   // threads of a staging memcpy (pageable callers)
     Lane lanes[3];
     cudaEvent_t dev_done = nullptr;   // completion of the last `_device` call (it owns lane 2's workspace until then)
     bool dev_used = false;

@@ -56,6 +56,11 @@ class Context {
     explicit Context(int device = 0, int fixed_window_bits = 0) {
         if (plume_ctx_create(&h_, device, fixed_window_bits) != PLUME_OK) throw Error(std::string("plume_ctx_create: ") + plume_last_error(nullptr));
     }
+    // one context over several GPUs: the batch calls range-split over them (plume_ctx_create_multi)
+    explicit Context(const std::vector<int>& devices, int fixed_window_bits = 0) {
+        if (plume_ctx_create_multi(&h_, devices.data(), (int)devices.size(), fixed_window_bits) != PLUME_OK)
+            throw Error(std::string("plume_ctx_create_multi: ") + plume_last_error(nullptr));
+    }
     ~Context() { plume_ctx_destroy(h_); }
     Context(const Context&) = delete;
     Context& operator=(const Context&) = delete;

@@ -15,6 +15,8 @@ SYMBOLS = {
     "plume_ctx_create_multi": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int]),
     "plume_ctx_device_count": (ctypes.c_int, [ctypes.c_void_p]),
     "plume_ctx_sub": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_int]),
+    "plume_shard_range": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t),
+                                         ctypes.POINTER(ctypes.c_size_t)]),
     "plume_ctx_destroy": (None, [ctypes.c_void_p]),
     "plume_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
     "plume_ctx_chunk_items": (ctypes.c_size_t, [ctypes.c_void_p]),

@@ -18,6 +18,10 @@ pub const PLUME_STATUS_H_INF: u8 = 5;
 extern "C" {
     pub fn plume_version() -> c_int;
     pub fn plume_ctx_create(out: *mut *mut plume_ctx, device: c_int, fixed_window_bits: c_int) -> c_int;
+    /// one context over several GPUs of this process: host-pointer batch calls range-split over them
+    pub fn plume_ctx_create_multi(out: *mut *mut plume_ctx, devices: *const c_int, n_devices: c_int, fixed_window_bits: c_int) -> c_int;
+    pub fn plume_ctx_device_count(ctx: *const plume_ctx) -> c_int;
+    pub fn plume_ctx_sub(ctx: *mut plume_ctx, i: c_int) -> *mut plume_ctx;
     pub fn plume_ctx_destroy(ctx: *mut plume_ctx);
     pub fn plume_last_error(ctx: *const plume_ctx) -> *const c_char;
     pub fn plume_ctx_chunk_items(ctx: *const plume_ctx) -> usize;
@@ -54,7 +58,8 @@ extern "C" {
     ) -> c_int;
     pub fn plume_hash_to_curve_witness_batch(
         ctx: *mut plume_ctx, n: usize, msgs: *const u8, msg_offsets: *const u64, msg_len: usize,
-        u: *mut u8, q: *mut u8, gx1_square: *mut u8, h: *mut u8,
+        u: *mut u8, q: *mut u8, gx1_square: *mut u8, h: *mut u8, hints: *mut u8,
     ) -> c_int;
+    pub fn plume_fixed_base_mul_batch(ctx: *mut plume_ctx, n: usize, scalars: *const u8, out: *mut u8) -> c_int;
     pub fn plume_registers_batch(ctx: *mut plume_ctx, n: usize, in32: *const u8, out4: *mut u64) -> c_int;
 }
