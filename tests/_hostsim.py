@@ -64,7 +64,7 @@ def ark_sign_batch(version, msgs, pk, sk, r, gw=8, binv_threads=3):
     o = {k: np.zeros((n, w), dtype=np.uint8) for k, w in
          (("nullifier", 64), ("digest_private", 32), ("s", 32), ("r_point", 64), ("hashed_to_curve_r", 64))}
     o["status"] = np.zeros(n, dtype=np.uint8)
-    lib().hs_sign_batch(1, 1, version, n, _p(blob), _p(offs), 0, _p(sk), _p(r), _p(pk), _p(o["nullifier"]), _p(o["digest_private"]),
+    lib().hs_sign_batch(1, 2, version, n, _p(blob), _p(offs), 0, _p(sk), _p(r), _p(pk), _p(o["nullifier"]), _p(o["digest_private"]),
                         _p(o["s"]), _p(o["r_point"]), _p(o["hashed_to_curve_r"]), _p(o["status"]), gw, binv_threads)
     return o
 
@@ -86,7 +86,7 @@ def sign_batch(version, msgs, sk, r, gw=8, binv_threads=3, comb=True):
     o = {k: np.zeros((n, w), dtype=np.uint8) for k, w in
          (("pk", 64), ("nullifier", 64), ("c", 32), ("s", 32), ("r_point", 64), ("hashed_to_curve_r", 64))}
     o["status"] = np.zeros(n, dtype=np.uint8)
-    lib().hs_sign_batch(0, 1 if comb else 0, version, n, _p(blob), _p(offs), 0, _p(sk), _p(r), _p(o["pk"]), _p(o["nullifier"]), _p(o["c"]), _p(o["s"]),
+    lib().hs_sign_batch(0, int(comb), version, n, _p(blob), _p(offs), 0, _p(sk), _p(r), _p(o["pk"]), _p(o["nullifier"]), _p(o["c"]), _p(o["s"]),
                         _p(o["r_point"]), _p(o["hashed_to_curve_r"]), _p(o["status"]), gw, binv_threads)
     return o
 

@@ -30,5 +30,23 @@ assert np.array_equal(w["h"], h)
 ctx.registers_batch(o["c"])
 c33 = ctx.points_compress(o["pk"])
 ctx.points_decompress(c33)
+ctx.fixed_base_mul_batch(sk)
+# fixed 32-byte and 65-byte records (the fixed-layout b0 path, word and byte loads), and a batch above the small-batch
+# threshold (no second stream) next to the ones above (second stream for G*s - pk*c)
+fixed = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+o = ctx.sign_batch(1, fixed, sk, r)
+ctx.verify_batch(1, fixed, o["pk"], o["nullifier"], o["c"], o["s"], o["r_point"], o["hashed_to_curve_r"])
+ctx.hash_to_curve_batch(rng.integers(0, 256, (n, 65), dtype=np.uint8))
+big = 9000
+bm = rng.integers(0, 256, (big, 32), dtype=np.uint8)
+bs = rng.integers(0, 256, (big, 32), dtype=np.uint8); bs[:, 0] &= 0x7F
+o = ctx.sign_batch(2, bm, bs, bs)
+assert ctx.verify_batch(2, bm, o["pk"], o["nullifier"], o["c"], o["s"]).all()
 ctx.close()
+# the multi-device context (one sub-context per visible GPU; worker threads)
+import torch
+m = P.PlumeContext(list(range(torch.cuda.device_count())), 8)
+o = m.sign_batch(1, msgs, sk, r)
+m.verify_batch(1, msgs, o["pk"], o["nullifier"], o["c"], o["s"], o["r_point"], o["hashed_to_curve_r"])
+m.close()
 print("done")

@@ -137,9 +137,17 @@ int hs_sign_batch(int flavour, int comb, int version, uint32_t n, const uint8_t*
     run_binv(a.ws, n, 2 * n, binv_threads);
     for (uint32_t i = 0; i < n; i++) sign_stage_h2c(i, a);
     run_binv(a.ws, n, n, binv_threads);
-    for (uint32_t i = 0; i < n; i++) {
-        if (comb) sign_stage_varbase_comb(i, a, tabw);
-        else sign_stage_varbase(i, a, tabw);
+    if (comb == 2) {   // the shipped split: table kernel, then one ladder thread per item and scalar
+        std::vector<uint32_t> tabs((size_t)n * VB_ITEM_WORDS);
+        a.vbtab = tabs.data();
+        for (uint32_t i = 0; i < n; i++) sign_stage_varbase_tab(i, a, tabs.data() + (size_t)i * VB_ITEM_WORDS);
+        for (uint32_t idx = 2 * n; idx-- > 0;) sign_stage_varbase_lad(idx, a, tabs.data());
+        a.vbtab = nullptr;
+    } else {
+        for (uint32_t i = 0; i < n; i++) {
+            if (comb) sign_stage_varbase_comb(i, a, tabw);
+            else sign_stage_varbase(i, a, tabw);
+        }
     }
     run_binv(a.ws, n, 2 * n, binv_threads);
     for (uint32_t i = 0; i < n; i++) sign_stage_final(i, a);
@@ -159,15 +167,16 @@ int hs_verify_batch(int flavour, int version, uint32_t n, const uint8_t* msgs, c
     a.ok = ok; a.ws = ws.data(); a.gtab = g_tab.data(); a.gw = gw; a.vbtab = nullptr;
     (void)fused;
     for (uint32_t i = 0; i < n; i++) verify_stage_h2c(i, a);
-    run_binv(a.ws, n, n, binv_threads);
+    for (uint32_t t = 0; t < binv_threads; t++) binv_body(t, binv_threads, ws_at(a.ws, n, WS_Z1, 0), ws_at(a.ws, n, WS_P0, 0), n);
     {
         // per-item table storage: the tables live from the table kernel to the ladder kernel
         std::vector<uint32_t> tabs((size_t)n * VB_ITEM_WORDS);
         auto t1 = [&](uint32_t i) { return tabs.data() + (size_t)i * VB_ITEM_WORDS; };
         auto t2 = [&](uint32_t i) { return tabs.data() + (size_t)i * VB_ITEM_WORDS + VB_TAB_WORDS; };
+        // G*s - pk*c first here (the library runs it last, or concurrently for small batches): the stages are independent
+        for (uint32_t i = 0; i < n; i++) verify_stage_mul_a(i, a, t2(i) + VB_TAB_WORDS);
         for (uint32_t i = 0; i < n; i++) verify_stage_mul_b1(i, a, t1(i), t2(i));
         for (uint32_t i = 0; i < n; i++) verify_stage_mul_b2(i, a, t1(i), t2(i));
-        for (uint32_t i = 0; i < n; i++) verify_stage_mul_a(i, a, t1(i));
     }
     run_binv(a.ws, n, 2 * n, binv_threads);
     for (uint32_t i = 0; i < n; i++) verify_stage_final(i, a);

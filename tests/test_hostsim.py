@@ -131,7 +131,7 @@ def test_h2c_pipeline(golden):
 def _check_sign_verify(ver, msgs, sks, rs, golden=None):
     skb = b"".join(x.to_bytes(32, "big") for x in sks); rb = b"".join(x.to_bytes(32, "big") for x in rs)
     want = c_oracle.sign_batch(ver, msgs, skb, rb, threads=2)
-    for comb in (True, False):   # the shipped signed comb, and the windowed ladder kept behind -DPLUME_SIGN_WINDOWED
+    for comb in (2, 1, 0):   # the shipped form (comb table kernel + ladder kernel), the comb as one kernel, the windowed ladder (-DPLUME_SIGN_WINDOWED)
         got = H.sign_batch(ver, msgs, skb, rb, gw=8, binv_threads=5, comb=comb)
         for k in ("status", "pk", "nullifier", "c", "s", "r_point", "hashed_to_curve_r"):
             assert np.array_equal(got[k], want[k]), (k, comb)

@@ -22,7 +22,7 @@ namespace {
 
 const char* const kStageNames[ST_COUNT] = {"sign_fixed", "sign_h2c", "sign_varbase", "sign_final", "verify_h2c", "verify_final",
                                            "h2c_map", "h2c_out", "binv", "sec1_compress", "sec1_decompress", "verify_mul_a",
-                                           "verify_mul_b", "h2c_witness", "registers", "verify_tab_b", "fixed_mul"};
+                                           "verify_mul_b", "h2c_witness", "registers", "verify_tab_b", "fixed_mul", "sign_tab"};
 
 thread_local std::string g_create_error;   // last plume_ctx_create* failure of THIS thread
 
@@ -86,8 +86,9 @@ int run_stage(plume_ctx* ctx, int stage, cudaStream_t s, F&& launch) {
         if (rc__ != PLUME_OK) return rc__;                                           \
     } while (0)
 
-int binv(plume_ctx* ctx, uint32_t* ws, uint32_t n, uint32_t m, cudaStream_t s) {
-    RUN(ST_BINV, launch_binv(ws + (size_t)WS_Z0 * n * 8, ws + (size_t)WS_P0 * n * 8, m, ctx->binv_k, s));
+// batched inversion of m workspace elements starting at slot `slot` (WS_Z0: both Z arrays when m = 2n; WS_Z1: the second)
+int binv(plume_ctx* ctx, uint32_t* ws, uint32_t n, uint32_t m, cudaStream_t s, int slot = WS_Z0) {
+    RUN(ST_BINV, launch_binv(ws + (size_t)slot * n * 8, ws + (size_t)WS_P0 * n * 8, m, ctx->binv_k, s));
     return PLUME_OK;
 }
 
@@ -96,19 +97,37 @@ int enqueue_sign(plume_ctx* ctx, sign_args a, cudaStream_t s) {
     if (int rc = binv(ctx, a.ws, a.n, 2 * a.n, s)) return rc;
     RUN(ST_SIGN_H2C, launch_sign_h2c(a, s));
     if (int rc = binv(ctx, a.ws, a.n, a.n, s)) return rc;
+#ifdef PLUME_SIGN_ONE_KERNEL
     RUN(ST_SIGN_VARBASE, launch_sign_varbase(a, s));
+#else
+    RUN(ST_SIGN_TAB, launch_sign_comb_tab(a, s));
+    RUN(ST_SIGN_VARBASE, launch_sign_comb_lad(a, s));
+#endif
     if (int rc = binv(ctx, a.ws, a.n, 2 * a.n, s)) return rc;
     RUN(ST_SIGN_FINAL, launch_sign_final(a, s));
     return PLUME_OK;
 }
+// Batches of at most this many items leave most of the GPU idle (one thread per item): their latency is the length of the
+// dependent chain of stages, so independent stages are put on two streams (verify: G*s - pk*c next to h*s - nul*c).
+const uint32_t kSmallBatch = 8192;
+
 int enqueue_verify(plume_ctx* ctx, verify_args a, cudaStream_t s) {
+    const bool fork = a.n <= kSmallBatch && ctx->aux_stream != nullptr;
     RUN(ST_VERIFY_H2C, launch_verify_h2c(a, s));
-    if (int rc = binv(ctx, a.ws, a.n, a.n, s)) return rc;
+    if (fork) {   // A needs the input checks of the first stage (ok[]) and nothing else: start it next to the stages of B
+        cudaStream_t sa = ctx->aux_stream;
+        CU(cudaEventRecord(ctx->ev_fork, s));
+        CU(cudaStreamWaitEvent(sa, ctx->ev_fork, 0));
+        if (int rc = run_stage(ctx, ST_VERIFY_MUL_A, sa, [&]() -> cudaError_t { return launch_verify_mul_a(a, sa); })) return rc;
+        CU(cudaEventRecord(ctx->ev_join, sa));
+    }
+    if (int rc = binv(ctx, a.ws, a.n, a.n, s, WS_Z1)) return rc;
     // separate kernels, each with its own register budget: one fused kernel needs 168 registers (12 warps/SM), the
     // ladders alone run at 128 or fewer (16-24 warps/SM); 18 % faster in total (round 1)
     RUN(ST_VERIFY_TAB_B, launch_verify_tab_b(a, s));
     RUN(ST_VERIFY_MUL_B, launch_verify_lad_b(a, s));
-    RUN(ST_VERIFY_MUL_A, launch_verify_mul_a(a, s));
+    if (fork) CU(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+    else RUN(ST_VERIFY_MUL_A, launch_verify_mul_a(a, s));
     if (int rc = binv(ctx, a.ws, a.n, 2 * a.n, s)) return rc;
     RUN(ST_VERIFY_FINAL, launch_verify_final(a, s));
     return PLUME_OK;
@@ -386,6 +405,9 @@ int ctx_create_single(plume_ctx** out, int device, int fixed_window_bits, const 
     struct Guard { plume_ctx* c; ~Guard() { if (c) plume_ctx_destroy(c); } } guard{c};
     for (int k = 0; k < 2; k++) CU(cudaStreamCreateWithFlags(&c->lanes[k].stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->dev_done, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     const int nwin = (256 + w - 1) / w;
     const size_t ne = (size_t)nwin << w;
     CU(cudaMalloc(&c->gtab, ne * 64));
@@ -448,6 +470,9 @@ void plume_ctx_destroy(plume_ctx* ctx) {
         if (L.stream) cudaStreamDestroy(L.stream);
     }
     if (ctx->dev_done) cudaEventDestroy(ctx->dev_done);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->gtab) cudaFree(ctx->gtab);
     delete ctx;
 }

@@ -13,7 +13,7 @@
 
 enum Stage { ST_SIGN_FIXED, ST_SIGN_H2C, ST_SIGN_VARBASE, ST_SIGN_FINAL, ST_VERIFY_H2C, ST_VERIFY_FINAL, ST_H2C_MAP, ST_H2C_OUT,
              ST_BINV, ST_SEC1_COMPRESS, ST_SEC1_DECOMPRESS, ST_VERIFY_MUL_A, ST_VERIFY_MUL_B, ST_H2C_WITNESS, ST_REGISTERS,
-             ST_VERIFY_TAB_B, ST_FIXED_MUL, ST_COUNT };
+             ST_VERIFY_TAB_B, ST_FIXED_MUL, ST_SIGN_TAB, ST_COUNT };
 
 struct PendingCopy { void* dst; const void* src; size_t bytes; };
 
@@ -47,6 +47,8 @@ struct plume_ctx {
     Lane lanes[3];
     cudaEvent_t dev_done = nullptr;   // completion of the last `_device` call (it owns lane 2's workspace until then)
     bool dev_used = false;
+    cudaStream_t aux_stream = nullptr;        // second stream of small batches (independent stages side by side)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     uint64_t launches = 0;
     bool profiling = false;

@@ -30,7 +30,9 @@
 
 cudaError_t launch_sign_fixed(const sign_args& a, cudaStream_t s);
 cudaError_t launch_sign_h2c(const sign_args& a, cudaStream_t s);
-cudaError_t launch_sign_varbase(const sign_args& a, cudaStream_t s);
+cudaError_t launch_sign_varbase(const sign_args& a, cudaStream_t s);    // table and ladders of h^r, h^sk in one kernel ...
+cudaError_t launch_sign_comb_tab(const sign_args& a, cudaStream_t s);   // ... or as two: the comb table (n threads)
+cudaError_t launch_sign_comb_lad(const sign_args& a, cudaStream_t s);   //     and the ladders (2n threads)
 cudaError_t launch_sign_final(const sign_args& a, cudaStream_t s);
 cudaError_t launch_verify_h2c(const verify_args& a, cudaStream_t s);
 cudaError_t launch_verify_tab_b(const verify_args& a, cudaStream_t s);   // the two window tables of h*s - nul*c (first: reads the inverted Z of h) ...

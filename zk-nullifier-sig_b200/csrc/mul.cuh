@@ -414,5 +414,6 @@ PLUME_DEV jac comb_mul_tab(const sc& k, const uint32_t* tab, const fe& zg, const
     return acc;
 }
 
-// scratch words per item: the signer's comb area or the verifier's two window tables, whichever is larger
-#define VB_ITEM_WORDS (COMB_AREA_WORDS > 2 * VB_TAB_WORDS ? COMB_AREA_WORDS : 2 * VB_TAB_WORDS)
+// scratch words per item: the signer's comb area or the verifier's three window tables (h and nul for h*s - nul*c, pk for
+// G*s - pk*c: separate, so that the two may run side by side), whichever is larger
+#define VB_ITEM_WORDS (COMB_AREA_WORDS > 3 * VB_TAB_WORDS ? COMB_AREA_WORDS : 3 * VB_TAB_WORDS)

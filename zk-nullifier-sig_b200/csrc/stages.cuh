@@ -406,6 +406,38 @@ PLUME_DEV void sign_stage_varbase_comb(uint32_t i, const sign_args& a, uint32_t*
     }
 }
 
+// The same stage as two kernels: the table (one thread per item) and the ladders (one thread per item AND scalar: 2n
+// threads, thread idx < n takes r, idx >= n takes sk of item idx - n).  Each kernel's code is one small loop nest, so the
+// instruction cache is not shared between warps in the table builder and warps in a ladder, and each gets its own register
+// budget.  Zg travels through WS_P0 (scratch of the batched inversion, idle here); Zg = 0 marks an item without ladders.
+PLUME_DEV void sign_stage_varbase_tab(uint32_t i, const sign_args& a, uint32_t* area) {
+    aff h = ws_load_affine(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i);
+    ws_store_aff(a.ws, a.n, WS_HX, WS_HY, i, h);
+    if (h.inf) {
+        a.status[i] = PLUME_ST_H_INF;   // the reference panics here (randomizedsigner.rs:61)
+        jac o = jac_infinity();
+        ws_store_jac(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i, o);
+        ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, o);
+        st_fe(ws_at(a.ws, a.n, WS_P0, i), fe_zero());
+        return;
+    }
+    st_fe(ws_at(a.ws, a.n, WS_P0, i), comb_build_table(h.x, h.y, area));
+}
+PLUME_DEV void sign_stage_varbase_lad(uint32_t idx, const sign_args& a, const uint32_t* vbtab) {
+    const uint32_t which = idx >= a.n ? 1u : 0u, i = idx - which * a.n;
+    fe zg = ld_fe(ws_at(a.ws, a.n, WS_P0, i));
+    if (fe_is_zero(zg)) return;   // h was the identity: the table stage stored the results
+    fe hx = ld_fe(ws_at(a.ws, a.n, WS_HX, i)), hy = ld_fe(ws_at(a.ws, a.n, WS_HY, i));
+    fe zg2 = fe_sqr(zg);
+    fe hxs = fe_mul(hx, zg2), hys = fe_mul(hy, fe_mul(zg2, zg));   // h on the table's isomorphic curve
+    sc k = ld_sc_be((which ? a.sk : a.r) + (size_t)i * 32);
+    const bool zero_ok = a.flavour == PLUME_FLAVOUR_ARKWORKS;
+    if (sc_ge_n(k) || (!zero_ok && sc_is_zero(k))) k = sc_one();
+    jac o = comb_mul_tab(k, vbtab + (size_t)i * VB_ITEM_WORDS, zg, hxs, hys);
+    if (which == 0) ws_store_jac(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i, o);
+    else ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, o);
+}
+
 // affine point read back from two workspace slots: (0, 0) is how the identity was stored (no curve point has y = 0)
 PLUME_DEV aff ws_load_aff_xy(uint32_t* ws, uint32_t n, int sx, int sy, uint32_t i) {
     aff p;
@@ -522,7 +554,9 @@ PLUME_DEV void verify_stage_h2c(uint32_t i, const verify_args& a) {
     uint32_t len;
     const uint8_t* m = msg_ptr(a.msgs, i, len);
     jac h = h2c_hash_to_curve(m, len, pk33, npk);  // lib.rs:103
-    ws_store_jac(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i, h);
+    // Z of h goes to WS_Z1 (inverted there, consumed by the table stage, later overwritten by B's Z): WS_Z0 belongs to
+    // A = G*s - pk*c alone, so that stage may run concurrently with the two stages of B (small batches: two streams)
+    ws_store_jac(a.ws, a.n, WS_HX, WS_HY, WS_Z1, i, h);
 }
 
 // k * P for an affine P that may be the identity
@@ -533,12 +567,12 @@ PLUME_DEV jac vb_mul_point(const aff& p, const sc& k, uint32_t* tab) {
 }
 
 // h*s - nul*c as two kernels: the table pair (b1) and the double-base ladder (b2), so that the ladder, which is
-// where the time goes, is compiled for 4 blocks per SM (b1 runs first: it consumes the inverted Z of h in WS_Z0, which
-// the result of G*s - pk*c later overwrites).  tab1, tab2: two table areas of this thread (global scratch).
+// where the time goes, is compiled for 4 blocks per SM (b1 consumes the inverted Z of h in WS_Z1, which b2 then
+// overwrites with the Z of the result).  tab1, tab2: two table areas of this thread (global scratch).
 // zg travels through WS_KX, the "ladder to do" flag through WS_RY;
 // the rare case of an identity among h, nul (adversarial inputs only) is finished inside b1.
 PLUME_DEV void verify_stage_mul_b1(uint32_t i, const verify_args& a, uint32_t* tab1, uint32_t* tab2) {
-    aff h = ws_load_affine(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i);
+    aff h = ws_load_affine(a.ws, a.n, WS_HX, WS_HY, WS_Z1, i);
     ws_store_aff(a.ws, a.n, WS_HX, WS_HY, i, h);
     st_fe(ws_at(a.ws, a.n, WS_RX, i), fe_set_u32(h.inf));
     const bool good = a.ok[i] != 0;
