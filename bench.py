@@ -415,7 +415,6 @@ def run_leg(env, workload, lg, steps, warmup, with_cpu_baseline=False, with_page
     sampler = ClockSampler(env.local_rank) if (clocks and rank == 0) else None
     if sampler:
         sampler.start()
-    ctx.set_profiling(True)
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(env.stream)
@@ -425,6 +424,17 @@ def run_leg(env, workload, lg, steps, warmup, with_cpu_baseline=False, with_page
     env.barrier()
     dev_ms = e0.elapsed_time(e1)
     launches = ctx.launch_count - launches0
+    # per-stage times: the same K steps once more with an event pair around every stage launch (plume_ctx_set_profiling).
+    # With the pairs on, the library runs each batch as ONE kernel sequence (no half-batch overlap), so a stage's time is the
+    # time of its kernel running alone on the GPU -- what the roofline of that kernel is about.
+    ctx.set_profiling(True)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(env.stream)
+    for _ in range(steps):
+        step_device(sign=timed_sign, verify=do_verify)
+    p1.record(env.stream)
+    env.barrier()
+    prof_ms = p0.elapsed_time(p1)
     stage = {}
     for st in ("sign_fixed", "sign_h2c", "sign_tab", "sign_varbase", "sign_final", "verify_h2c", "verify_mul_a", "verify_tab_b", "verify_mul_b",
                "verify_final", "h2c_map", "h2c_out", "binv", "sec1_compress", "sec1_decompress"):
@@ -568,6 +578,19 @@ def run_leg(env, workload, lg, steps, warmup, with_cpu_baseline=False, with_page
                                            "(SURVEY.md 8d counts, squarings at 44 instead of 72), %d items per launch"
                                            % (WORK_MS[kind][0], LP_PER_M, WORK_MS[kind][1], LP_PER_S, per_launch_items),
                        "avg_launch_ms": avg_ms}
+    # the same fraction for every kernel with an algorithmic count (the two kernels of the signer's h^r, h^sk together)
+    per_kernel = {}
+    for st_name, st_kind in (("sign_varbase", "sign_varbase"), ("verify_mul_a", "verify_mul_a"), ("verify_mul_b", "verify_mul_b"),
+                             ("verify_tab_b", "verify_tab_b"), ("sign_h2c", "h2c_map"), ("verify_h2c", "h2c_map"), ("h2c_map", "h2c_map"),
+                             ("sign_fixed", "fixed_pair")):
+        if st_name in stage:
+            t = stage[st_name]["ms_total"] / stage[st_name]["launches"]
+            label = st_name
+            if st_name == "sign_varbase" and "sign_tab" in stage:
+                t += stage["sign_tab"]["ms_total"] / stage["sign_tab"]["launches"]
+                label = "sign_tab+sign_varbase"
+            per_kernel[label] = {"ms": round(t, 3), "frac": round(per_launch_items * work_lp(st_kind) / (t * 1e-3) / peak_lp, 4)}
+    rec["roofline"]["per_kernel"] = per_kernel
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     gbs = per_launch_items * BYTES.get(dom, 160) / (avg_ms * 1e-3) / 1e9
     rec["roofline"]["hbm"] = {"achieved_gbs": gbs, "peak_gbs": hbm_peak, "frac": gbs / hbm_peak,
@@ -578,6 +601,10 @@ def run_leg(env, workload, lg, steps, warmup, with_cpu_baseline=False, with_page
     for key, su in (("whole_step_frac", False), ("whole_step_frac_survey_units", True)):
         rec["roofline"][key] = (n * sum(work_lp(k, su) for k in kinds) * steps / (dev_ms * 1e-3)) / peak_lp
     rec["stages"] = stage
+    rec["stages_note"] = ("per-stage CUDA-event times of a second pass of the same %d steps with an event pair around every stage "
+                          "launch; in that pass each batch is one kernel sequence (%.2f ms per step), in the timed region above large "
+                          "device-resident batches run as two half-batches on two streams so that one's kernels fill the other's "
+                          "partly filled last waves" % (steps, prof_ms / steps))
     if clk is not None:
         rec["clocks"] = clk
     # cpu baseline, bounded sample, rank 0 only at N = 1

@@ -74,8 +74,8 @@ int plume_version(void);
 
 /* Create a context on CUDA device `device` (ordinal as seen by the CUDA runtime in this
  * process).  Builds the fixed-base table for the generator on the device (one-off, ~0.1 s).
- * `fixed_window_bits` = 0 picks the default (20: a 872 MB table, 13 additions per multiplication); otherwise 4..22
- * (16 = 64 MiB that stay in the L2, 16 additions).
+ * `fixed_window_bits` = 0 picks the default (22: a 3.2 GB table, 12 additions per multiplication, built in ~0.4 s);
+ * otherwise 4..24 (16 = 64 MiB that stay in the L2, 16 additions; 20 = 872 MB, 13 additions, ~0.1 s).
  * A multi-GPU job is one process (context) per GPU, each given its contiguous range of the
  * batch; nothing is shared between contexts. */
 int plume_ctx_create(plume_ctx** out, int device, int fixed_window_bits);

@@ -5,6 +5,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <thread>
 
 #include "ctx.h"
@@ -154,23 +158,83 @@ bool is_pinned(const void* p) {
     return at.type == cudaMemoryTypeHost;
 }
 
-// memcpy between a caller's pageable array and the pinned staging arena; large copies are cut over a few threads
-// (one thread moves ~10 GB/s, which a 2^20-item V1 batch -- 0.8 GB in and out -- would feel)
-void stage_copy(const plume_ctx* ctx, void* dst, const void* src, size_t bytes) {
-    const size_t kMin = (size_t)4 << 20;
-    int t = ctx->stage_threads;
-    if (bytes < 2 * kMin || t <= 1) { memcpy(dst, src, bytes); return; }
-    if ((size_t)t > bytes / kMin) t = (int)(bytes / kMin);
+// memcpy between a caller's pageable arrays and the pinned staging arena.  One thread moves ~10 GB/s, which a 2^20-item V1
+// batch (0.8 GB in and out per sign + verify) would feel, so the copies of a chunk are cut into slices and shared between the
+// calling thread and a small persistent pool (threads are not spawned per copy: a chunk has seven arrays).
+}  // namespace
+struct CopyPool {
+    struct Job { char* dst; const char* src; size_t len; };
     std::vector<std::thread> th;
-    const size_t per = ((bytes / t) + 4095) & ~(size_t)4095;
-    for (int k = 1; k < t; k++) {
-        size_t o = (size_t)k * per;
-        if (o >= bytes) break;
-        size_t len = (o + per > bytes) ? bytes - o : per;
-        th.emplace_back([=] { memcpy((char*)dst + o, (const char*)src + o, len); });
+    std::mutex mu;
+    std::condition_variable cv, cv_done;
+    std::deque<Job> q;
+    size_t in_flight = 0;
+    bool quit = false;
+    explicit CopyPool(int workers) {
+        for (int i = 0; i < workers; i++) th.emplace_back([this] { loop(); });
     }
-    memcpy(dst, src, per < bytes ? per : bytes);
-    for (auto& x : th) x.join();
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> g(mu); quit = true; }
+        cv.notify_all();
+        for (auto& t : th) t.join();
+    }
+    bool take(Job& j) {   // mu held
+        if (q.empty()) return false;
+        j = q.front();
+        q.pop_front();
+        return true;
+    }
+    void loop() {
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv.wait(lk, [this] { return quit || !q.empty(); });
+            if (quit) return;
+            Job j;
+            while (take(j)) {
+                lk.unlock();
+                memcpy(j.dst, j.src, j.len);
+                lk.lock();
+                if (--in_flight == 0) cv_done.notify_all();
+            }
+        }
+    }
+    // copy everything in `jobs` (sliced), the caller working along; returns when all of it is in place
+    void run(const std::vector<Job>& jobs) {
+        const size_t kSlice = (size_t)2 << 20;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            for (const Job& j : jobs)
+                for (size_t o = 0; o < j.len; o += kSlice) {
+                    q.push_back({j.dst + o, j.src + o, j.len - o < kSlice ? j.len - o : kSlice});
+                    in_flight++;
+                }
+        }
+        cv.notify_all();
+        std::unique_lock<std::mutex> lk(mu);
+        Job j;
+        while (take(j)) {
+            lk.unlock();
+            memcpy(j.dst, j.src, j.len);
+            lk.lock();
+            --in_flight;
+        }
+        cv_done.wait(lk, [this] { return in_flight == 0; });
+    }
+};
+namespace {
+void stage_copy_many(plume_ctx* ctx, const std::vector<CopyPool::Job>& jobs) {
+    size_t total = 0;
+    for (const auto& j : jobs) total += j.len;
+    if (total == 0) return;
+    if (total < ((size_t)4 << 20) || ctx->stage_threads <= 1) {
+        for (const auto& j : jobs) memcpy(j.dst, j.src, j.len);
+        return;
+    }
+    if (!ctx->copy_pool) ctx->copy_pool = new CopyPool(ctx->stage_threads - 1);
+    ctx->copy_pool->run(jobs);
+}
+void stage_copy(plume_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    stage_copy_many(ctx, {{(char*)dst, (const char*)src, bytes}});
 }
 
 // ---- lane storage ---------------------------------------------------------------------------------------
@@ -252,7 +316,11 @@ void lane_wipe_host(Lane& L) {
 int lane_finish(plume_ctx* ctx, Lane& L) {
     if (!L.busy) return PLUME_OK;
     CU(cudaStreamSynchronize(L.stream));
-    for (const PendingCopy& p : L.pending) stage_copy(ctx, p.dst, p.src, p.bytes);
+    if (!L.pending.empty()) {   // all staged outputs of the chunk in one parallel copy
+        std::vector<CopyPool::Job> jobs;
+        for (const PendingCopy& p : L.pending) jobs.push_back({(char*)p.dst, (const char*)p.src, p.bytes});
+        stage_copy_many(ctx, jobs);
+    }
     L.pending.clear();
     lane_wipe_host(L);
     L.busy = false;
@@ -359,6 +427,35 @@ int dev_end(plume_ctx* ctx, cudaStream_t s) {
     return PLUME_OK;
 }
 
+// A large device-resident batch runs as TWO half-batches, the second on the context's auxiliary stream: every stage kernel
+// ends with a partly filled last wave (2^20 items are 9.2 waves of the 6-blocks-per-SM kernels), and with two independent
+// kernel sequences in flight the blocks of one fill the SMs the other's tail leaves idle -- the same effect the two lanes of
+// the host-pointer path get for free.  Not while per-stage profiling is on (the event pairs would time overlapping kernels).
+const size_t kSplitMin = 1 << 16;
+template <class F>
+int dev_run(plume_ctx* ctx, size_t n, cudaStream_t s, F&& part) {
+    if (int rc = dev_begin(ctx, n, s)) return rc;
+    Lane& L = ctx->lanes[2];
+    if (!ctx->dev_split || ctx->profiling || n < kSplitMin) {
+        if (int rc = part(0, n, L.ws, L.vbtab, s)) return rc;
+    } else {
+        const size_t n1 = ((n / 2) + 127) & ~(size_t)127;
+        cudaStream_t sa = ctx->aux_stream;
+        CU(cudaEventRecord(ctx->ev_fork, s));
+        CU(cudaStreamWaitEvent(sa, ctx->ev_fork, 0));
+        if (int rc = part(0, n1, L.ws, L.vbtab, s)) return rc;
+        if (int rc = part(n1, n - n1, L.ws + (size_t)WS_SLOTS * n1 * 8, L.vbtab + n1 * (size_t)VB_ITEM_WORDS, sa)) return rc;
+        CU(cudaEventRecord(ctx->ev_join, sa));
+        CU(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+    }
+    return dev_end(ctx, s);
+}
+
+template <class T> T* at(T* p, size_t first, size_t width) { return p ? p + first * width : nullptr; }
+// message arguments of the items from `first` on: fixed-length records move the base, an offsets array moves the offsets
+const uint8_t* msgs_at(const uint8_t* msgs, const uint64_t* offs, size_t msg_len, size_t first) { return (offs || !msgs) ? msgs : msgs + first * msg_len; }
+const uint64_t* offs_at(const uint64_t* offs, size_t first) { return offs ? offs + first : nullptr; }
+
 struct DevBuf {   // temporaries of plume_ctx_create: freed on every exit path
     void* p = nullptr;
     ~DevBuf() { if (p) cudaFree(p); }
@@ -379,10 +476,11 @@ int ctx_create_single(plume_ctx** out, int device, int fixed_window_bits, const 
     if (e != cudaSuccess || ndev == 0)
         return fail(nullptr, PLUME_E_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
     if (device < 0 || device >= ndev) return fail(nullptr, PLUME_E_NO_DEVICE, "device ordinal out of range");
-    // default 20 bits: 13 windows x 2^20 affine points = 872 MB of HBM, 13 additions per fixed-base multiplication
-    // (16 bits: 64 MiB, 16 additions; measured sign_fixed 3.44 -> 2.79 ms and verify_mul_a 19.46 -> 19.03 ms per 2^20 items)
-    int w = fixed_window_bits ? fixed_window_bits : (int)env_size("PLUME_FIXED_WINDOW", 20);
-    if (w < 4 || w > 22) return fail(nullptr, PLUME_E_ARG, "fixed_window_bits must be in 4..22");
+    // default 22 bits: 12 windows x 2^22 affine points = 3.2 GB of HBM, 12 additions per fixed-base multiplication (180 GB
+    // per GPU is there to be used).  Measured per 2^20 items, sign_fixed / verify_mul_a: 16 bits (64 MiB, 16 additions)
+    // 3.44 / 19.46 ms, 18 bits 3.22 / 19.05, 20 bits (872 MB, 13) 2.78 / 18.81, 22 bits 2.55 / 18.69.
+    int w = fixed_window_bits ? fixed_window_bits : (int)env_size("PLUME_FIXED_WINDOW", 22);
+    if (w < 4 || w > 24) return fail(nullptr, PLUME_E_ARG, "fixed_window_bits must be in 4..24");
     ScopedDevice sd(device);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
@@ -400,8 +498,9 @@ int ctx_create_single(plume_ctx** out, int device, int fixed_window_bits, const 
     // the last download of a call -- the part the two lanes cannot overlap -- are a small fraction of it
     c->host_chunk = env_size("PLUME_HOST_CHUNK_ITEMS", (size_t)prop.multiProcessorCount * 128 * 12);
     if (c->host_chunk > c->chunk) c->host_chunk = c->chunk;
-    c->binv_k = (uint32_t)env_size("PLUME_BINV_K", 16);
+    c->binv_k = (uint32_t)env_size("PLUME_BINV_K", 32);   // elements per inversion: 8 -> 0.42 ms per 2^21 elements, 16 -> 0.27, 32 -> 0.21, 64 -> 0.21
     c->stage_threads = (int)env_size("PLUME_STAGE_THREADS", 8);
+    { const char* v = getenv("PLUME_DEVICE_SPLIT"); c->dev_split = !(v && v[0] == '0'); }
     struct Guard { plume_ctx* c; ~Guard() { if (c) plume_ctx_destroy(c); } } guard{c};
     for (int k = 0; k < 2; k++) CU(cudaStreamCreateWithFlags(&c->lanes[k].stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->dev_done, cudaEventDisableTiming));
@@ -469,6 +568,7 @@ void plume_ctx_destroy(plume_ctx* ctx) {
         if (L.vbtab) cudaFree(L.vbtab);
         if (L.stream) cudaStreamDestroy(L.stream);
     }
+    delete ctx->copy_pool;
     if (ctx->dev_done) cudaEventDestroy(ctx->dev_done);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -616,15 +716,16 @@ int sign_device(plume_ctx* ctx, int flavour, int version, size_t n, const uint8_
     if (!sk || !r || !nullifier || !c || !s_out || !status) return fail(ctx, PLUME_E_ARG, "null array");
     if (flavour == PLUME_FLAVOUR_ARKWORKS ? !pk_in : !pk) return fail(ctx, PLUME_E_ARG, "null pk array");
     ScopedDevice sd(ctx->device);
-    if (int rc = dev_begin(ctx, n, (cudaStream_t)stream)) return rc;
-    sign_args a{};
-    a.version = version; a.flavour = flavour; a.n = (uint32_t)n;
-    a.msgs.base = msgs; a.msgs.offs = msg_offsets; a.msgs.fixed_len = (uint32_t)msg_len;
-    a.sk = sk; a.r = r; a.pk = pk; a.pk_in = pk_in; a.nullifier = nullifier; a.c = c; a.s = s_out; a.r_point = r_point;
-    a.hashed_to_curve_r = hashed_to_curve_r; a.status = status;
-    a.ws = ctx->lanes[2].ws; a.gtab = ctx->gtab; a.gw = ctx->gw; a.vbtab = ctx->lanes[2].vbtab;
-    if (int rc = enqueue_sign(ctx, a, (cudaStream_t)stream)) return rc;
-    return dev_end(ctx, (cudaStream_t)stream);
+    return dev_run(ctx, n, (cudaStream_t)stream, [&](size_t f, size_t k, uint32_t* ws, uint32_t* vbtab, cudaStream_t s) -> int {
+        sign_args a{};
+        a.version = version; a.flavour = flavour; a.n = (uint32_t)k;
+        a.msgs.base = msgs_at(msgs, msg_offsets, msg_len, f); a.msgs.offs = offs_at(msg_offsets, f); a.msgs.fixed_len = (uint32_t)msg_len;
+        a.sk = at(sk, f, 32); a.r = at(r, f, 32); a.pk = at(pk, f, 64); a.pk_in = at(pk_in, f, 64); a.nullifier = at(nullifier, f, 64);
+        a.c = at(c, f, 32); a.s = at(s_out, f, 32); a.r_point = at(r_point, f, 64);
+        a.hashed_to_curve_r = at(hashed_to_curve_r, f, 64); a.status = at(status, f, 1);
+        a.ws = ws; a.gtab = ctx->gtab; a.gw = ctx->gw; a.vbtab = vbtab;
+        return enqueue_sign(ctx, a, s);
+    });
 }
 int verify_device(plume_ctx* ctx, int flavour, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
                   const uint8_t* pk, const uint8_t* nullifier, const uint8_t* c, const uint8_t* s_in, const uint8_t* r_point,
@@ -639,14 +740,15 @@ int verify_device(plume_ctx* ctx, int flavour, int version, size_t n, const uint
     if ((version == 1 || flavour == PLUME_FLAVOUR_ARKWORKS) && (!r_point || !hashed_to_curve_r))
         return fail(ctx, PLUME_E_ARG, "r_point and hashed_to_curve_r are required");
     ScopedDevice sd(ctx->device);
-    if (int rc = dev_begin(ctx, n, (cudaStream_t)stream)) return rc;
-    verify_args a{};
-    a.version = version; a.flavour = flavour; a.n = (uint32_t)n;
-    a.msgs.base = msgs; a.msgs.offs = msg_offsets; a.msgs.fixed_len = (uint32_t)msg_len;
-    a.pk = pk; a.nullifier = nullifier; a.c = c; a.s = s_in; a.r_point = r_point; a.hashed_to_curve_r = hashed_to_curve_r;
-    a.ok = ok; a.ws = ctx->lanes[2].ws; a.gtab = ctx->gtab; a.gw = ctx->gw; a.vbtab = ctx->lanes[2].vbtab;
-    if (int rc = enqueue_verify(ctx, a, (cudaStream_t)stream)) return rc;
-    return dev_end(ctx, (cudaStream_t)stream);
+    return dev_run(ctx, n, (cudaStream_t)stream, [&](size_t f, size_t k, uint32_t* ws, uint32_t* vbtab, cudaStream_t s) -> int {
+        verify_args a{};
+        a.version = version; a.flavour = flavour; a.n = (uint32_t)k;
+        a.msgs.base = msgs_at(msgs, msg_offsets, msg_len, f); a.msgs.offs = offs_at(msg_offsets, f); a.msgs.fixed_len = (uint32_t)msg_len;
+        a.pk = at(pk, f, 64); a.nullifier = at(nullifier, f, 64); a.c = at(c, f, 32); a.s = at(s_in, f, 32);
+        a.r_point = at(r_point, f, 64); a.hashed_to_curve_r = at(hashed_to_curve_r, f, 64);
+        a.ok = at(ok, f, 1); a.ws = ws; a.gtab = ctx->gtab; a.gw = ctx->gw; a.vbtab = vbtab;
+        return enqueue_verify(ctx, a, s);
+    });
 }
 }  // namespace
 
@@ -689,23 +791,19 @@ int plume_hash_to_curve_batch_device(plume_ctx* ctx, size_t n, const uint8_t* ms
     if (n > ctx->chunk) return fail(ctx, PLUME_E_ARG, "n exceeds plume_ctx_chunk_items()");
     if (!out) return fail(ctx, PLUME_E_ARG, "null array");
     ScopedDevice sd(ctx->device);
-    if (int rc = dev_begin(ctx, n, (cudaStream_t)stream)) return rc;
-    h2c_args a;
-    a.n = (uint32_t)n;
-    a.msgs.base = msgs; a.msgs.offs = msg_offsets; a.msgs.fixed_len = (uint32_t)msg_len;
-    a.out = out; a.ws = ctx->lanes[2].ws;
-    if (int rc = enqueue_h2c(ctx, a, (cudaStream_t)stream)) return rc;
-    return dev_end(ctx, (cudaStream_t)stream);
+    return dev_run(ctx, n, (cudaStream_t)stream, [&](size_t f, size_t k, uint32_t* ws, uint32_t*, cudaStream_t s) -> int {
+        h2c_args a;
+        a.n = (uint32_t)k;
+        a.msgs.base = msgs_at(msgs, msg_offsets, msg_len, f); a.msgs.offs = offs_at(msg_offsets, f); a.msgs.fixed_len = (uint32_t)msg_len;
+        a.out = at(out, f, 64); a.ws = ws;
+        return enqueue_h2c(ctx, a, s);
+    });
 }
 
 // ---- host-pointer variants: chunked, two lanes in flight --------------------------------------------------------
 }  // extern "C" (reopened below)
 
 namespace {
-template <class T> T* at(T* p, size_t first, size_t width) { return p ? p + first * width : nullptr; }
-// message arguments of the items from `first` on: fixed-length records move the base, an offsets array moves the offsets
-const uint8_t* msgs_at(const uint8_t* msgs, const uint64_t* offs, size_t msg_len, size_t first) { return (offs || !msgs) ? msgs : msgs + first * msg_len; }
-const uint64_t* offs_at(const uint64_t* offs, size_t first) { return offs ? offs + first : nullptr; }
 
 int sign_host(plume_ctx* ctx, int flavour, int version, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
               const uint8_t* pk_in, const uint8_t* sk, const uint8_t* r, uint8_t* pk, uint8_t* nullifier, uint8_t* c, uint8_t* s_out,

@@ -34,7 +34,8 @@ struct Lane {
     bool busy = false;
 };
 
-struct Worker;   // api_multi.cu
+struct Worker;     // api_multi.cu
+struct CopyPool;   // api.cu: the staging copy threads of pageable callers
 
 struct plume_ctx {
     int device = 0;
@@ -42,11 +43,13 @@ struct plume_ctx {
     uint32_t* gtab = nullptr;
     size_t chunk = 0;        // largest n of one pass (what the `_device` entry points accept)
     size_t host_chunk = 0;   // pipelining granularity of the host-pointer entry points
-    uint32_t binv_k = 16;
+    uint32_t binv_k = 32;
     int stage_threads = 8;   // threads of a staging memcpy (pageable callers)
+    CopyPool* copy_pool = nullptr;   // created when the first pageable pointer shows up
     Lane lanes[3];
     cudaEvent_t dev_done = nullptr;   // completion of the last `_device` call (it owns lane 2's workspace until then)
     bool dev_used = false;
+    bool dev_split = true;            // large `_device` batches as two half-batches on two streams (PLUME_DEVICE_SPLIT=0: off)
     cudaStream_t aux_stream = nullptr;        // second stream of small batches (independent stages side by side)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;

@@ -18,10 +18,10 @@ __global__ void __launch_bounds__(VB_BLOCK, PLUME_VB_MINBLOCKS) k_sign_varbase(s
 #endif
 }
 #ifndef PLUME_ST_MINBLOCKS
-#define PLUME_ST_MINBLOCKS 5   // comb table per 2^20 items: 4 blocks/SM 9.94 ms, 5: 9.86, 6: 9.92
+#define PLUME_ST_MINBLOCKS 6   // comb table per 2^20 items: 4 blocks/SM 9.94 ms, 5: 9.86, 6: 9.92; 6 keeps the host path's 227 328-item chunks at whole waves
 #endif
 #ifndef PLUME_SL_MINBLOCKS
-#define PLUME_SL_MINBLOCKS 5   // comb ladders (2^21 threads): 4 blocks/SM 16.06 ms, 5: 15.62, 6: 15.69
+#define PLUME_SL_MINBLOCKS 6   // comb ladders (2^21 threads): 4 blocks/SM 16.06 ms, 5: 15.62, 6: 15.69 (whole waves per host chunk, as above)
 #endif
 __global__ void __launch_bounds__(VB_BLOCK, PLUME_ST_MINBLOCKS) k_sign_comb_tab(sign_args a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

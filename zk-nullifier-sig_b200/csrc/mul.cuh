@@ -131,11 +131,15 @@ PLUME_DEV fe vb_build_table(const fe& px, const fe& py, uint32_t* tab, bool fini
     fe ratio = fe_one();
 #pragma unroll 1
     for (int k = 7; k >= 1; k--) {
-        ratio = (k == 7) ? hs[7] : fe_mul(ratio, hs[k]);  // Z_8 / Z_k
         uint32_t* e = tab + (k - 1) * VB_ENT_WORDS;
+        // the raw entry was stored a while ago and comes back from the L2: ask for it before the three field operations
+        // that do not need it (40 % of this loop's stall samples were waits on these loads when they sat next to their use)
+        const fe x0 = ent_ld_fe(e), y0 = ent_ld_fe(e + 8);
+        ratio = (k == 7) ? hs[7] : fe_mul(ratio, hs[k]);  // Z_8 / Z_k
         fe r2 = fe_sqr(ratio);
-        fe x = fe_mul(ent_ld_fe(e), r2);
-        fe y = fe_mul(ent_ld_fe(e + 8), fe_mul(r2, ratio));
+        fe r3 = fe_mul(r2, ratio);
+        fe x = fe_mul(x0, r2);
+        fe y = fe_mul(y0, r3);
         if (finish) ent_finish(e, x, y);
         else ent_store_xy(e, x, y);
     }
@@ -160,8 +164,10 @@ PLUME_DEV jac vb_mul_tab(const sc& k, const uint32_t* tab, const fe& zg) {
     jac acc = jac_infinity();
 #pragma unroll 1
     for (int i = 32; i >= 0; i--) {
+        if (i < 32) {   // the accumulator is still the identity in the top window: nothing to double
 #pragma unroll 1
-        for (int j = 0; j < 4; j++) acc = jac_dbl_fast(acc);
+            for (int j = 0; j < 4; j++) acc = jac_dbl_fast(acc);
+        }
         int d1 = booth_next(b1);
         int d2 = booth_next(b2);
         // one addition body for both halves (the loop is kept rolled on purpose: code size)
@@ -182,8 +188,10 @@ PLUME_DEV jac vb_mul2_tab(const sc& k1, const uint32_t* tab1, const sc& k2, cons
     jac acc = jac_infinity();
 #pragma unroll 1
     for (int i = 32; i >= 0; i--) {
+        if (i < 32) {   // the accumulator is still the identity in the top window: nothing to double
 #pragma unroll 1
-        for (int j = 0; j < 4; j++) acc = jac_dbl_fast(acc);
+            for (int j = 0; j < 4; j++) acc = jac_dbl_fast(acc);
+        }
         int d0 = booth_next(b0), d1 = booth_next(b1), d2 = booth_next(b2), d3 = booth_next(b3);
         // one addition body for the four half-scalars (rolled on purpose: code size)
 #pragma unroll 1
@@ -206,11 +214,14 @@ PLUME_DEV fe vb_build_table_pair(const fe& p1x, const fe& p1y, uint32_t* tab1, c
     fe qx = fe_mul(p2x, z1_2);
     fe qy = fe_mul(p2y, fe_mul(z1_2, z1));
     fe z2 = vb_build_table(qx, qy, tab2, true);
+    fe x0 = ent_ld_fe(tab1), y0 = ent_ld_fe(tab1 + 8);
     fe z2_2 = fe_sqr(z2), z2_3 = fe_mul(z2_2, z2);
 #pragma unroll 1
     for (int e = 0; e < 8; e++) {
         uint32_t* t = tab1 + e * VB_ENT_WORDS;
-        ent_finish(t, fe_mul(ent_ld_fe(t), z2_2), fe_mul(ent_ld_fe(t + 8), z2_3));
+        const fe xc = x0, yc = y0;
+        if (e < 7) { x0 = ent_ld_fe(t + VB_ENT_WORDS); y0 = ent_ld_fe(t + VB_ENT_WORDS + 8); }   // next entry: in flight during this one
+        ent_finish(t, fe_mul(xc, z2_2), fe_mul(yc, z2_3));
     }
     return fe_mul(z1, z2);
 }
@@ -337,14 +348,14 @@ PLUME_DEV fe comb_build_table(const fe& px, const fe& py, uint32_t* area) {
     fe suf = fe_one();                            // z_{k+1} ... z_{NZ-1}
 #pragma unroll 1
     for (int k = COMB_NZ - 1; k >= 0; k--) {
+        uint32_t* e0 = tab + (2 * k) * VB_ENT_WORDS;
+        const fe xa = ent_ld_fe(e0), ya = ent_ld_fe(e0 + 8);   // raw leaves, back from the L2: requested before the products below
+        const fe xb = ent_ld_fe(e0 + VB_ENT_WORDS), yb = ent_ld_fe(e0 + VB_ENT_WORDS + 8);
         fe f = (k == COMB_NZ - 1) ? pre[k] : (k == 0 ? suf : fe_mul(pre[k], suf));
         suf = (k == COMB_NZ - 1) ? zs[k] : fe_mul(suf, zs[k]);
         fe f2 = fe_sqr(f), f3 = fe_mul(f2, f);
-#pragma unroll 1
-        for (int t = 0; t < 2; t++) {
-            uint32_t* e = tab + (2 * k + t) * VB_ENT_WORDS;
-            ent_finish(e, fe_mul(ent_ld_fe(e), f2), fe_mul(ent_ld_fe(e + 8), f3));
-        }
+        ent_finish(e0, fe_mul(xa, f2), fe_mul(ya, f3));
+        ent_finish(e0 + VB_ENT_WORDS, fe_mul(xb, f2), fe_mul(yb, f3));
     }
     return fe_mul(zc, zg);
 }
@@ -396,7 +407,7 @@ PLUME_DEV jac comb_mul_tab(const sc& k, const uint32_t* tab, const fe& zg, const
     jac acc = jac_infinity();
 #pragma unroll 1
     for (int c = COMB_D - 1; c >= 0; c--) {
-        acc = jac_dbl_fast(acc);
+        if (c < COMB_D - 1) acc = jac_dbl_fast(acc);   // (the identity in the top column: nothing to double)
 #pragma unroll 1
         for (int h = 0; h < 2; h++) acc = comb_add_column(acc, h ? r2 : r1, c, h != 0, tab);
     }
