@@ -436,7 +436,7 @@ def run_leg(env, workload, lg, steps, warmup, with_cpu_baseline=False, with_page
     env.barrier()
     prof_ms = p0.elapsed_time(p1)
     stage = {}
-    for st in ("sign_fixed", "sign_h2c", "sign_tab", "sign_varbase", "sign_final", "verify_h2c", "verify_mul_a", "verify_tab_b", "verify_mul_b",
+    for st in ("sign_fixed", "sign_h2c", "sign_tab", "sign_varbase", "sign_final", "verify_h2c", "verify_tab_a", "verify_mul_a", "verify_tab_b", "verify_mul_b",
                "verify_final", "h2c_map", "h2c_out", "binv", "sec1_compress", "sec1_decompress"):
         ms, k = ctx.stage_ms(st)
         if k:
@@ -581,14 +581,16 @@ def run_leg(env, workload, lg, steps, warmup, with_cpu_baseline=False, with_page
     # the same fraction for every kernel with an algorithmic count (the two kernels of the signer's h^r, h^sk together)
     per_kernel = {}
     for st_name, st_kind in (("sign_varbase", "sign_varbase"), ("verify_mul_a", "verify_mul_a"), ("verify_mul_b", "verify_mul_b"),
-                             ("verify_tab_b", "verify_tab_b"), ("sign_h2c", "h2c_map"), ("verify_h2c", "h2c_map"), ("h2c_map", "h2c_map"),
-                             ("sign_fixed", "fixed_pair")):
+                             ("verify_tab_b", "verify_tab_b"), ("sign_h2c", "h2c_map"), ("verify_h2c", "h2c_map"), ("h2c_map", "h2c_map")):
         if st_name in stage:
             t = stage[st_name]["ms_total"] / stage[st_name]["launches"]
             label = st_name
             if st_name == "sign_varbase" and "sign_tab" in stage:
                 t += stage["sign_tab"]["ms_total"] / stage["sign_tab"]["launches"]
                 label = "sign_tab+sign_varbase"
+            if st_name == "verify_mul_a" and "verify_tab_a" in stage:
+                t += stage["verify_tab_a"]["ms_total"] / stage["verify_tab_a"]["launches"]
+                label = "verify_tab_a+verify_mul_a"
             per_kernel[label] = {"ms": round(t, 3), "frac": round(per_launch_items * work_lp(st_kind) / (t * 1e-3) / peak_lp, 4)}
     rec["roofline"]["per_kernel"] = per_kernel
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
