@@ -33,6 +33,8 @@ int main(int argc, char** argv) {
     printf("v1 %s %s %d %d\n", hex(s1.c).c_str(), hex(s1.s).c_str(), (int)s1.verify(), (int)s1.v1specific.has_value());
     auto s2 = plume::PlumeSignature::sign_v2(sk, msg, rng);
     printf("v2 %s %s %d %d\n", hex(s2.c).c_str(), hex(s2.s).c_str(), (int)s2.verify(), (int)s2.v1specific.has_value());
+    printf("json1 %s\n", s1.to_json().c_str());
+    printf("json2 %s\n", s2.to_json().c_str());
     s2.s[31] ^= 1;
     printf("tampered %d\n", (int)s2.verify());
     // out-of-range secret key is rejected the way SecretKey::from_bytes does

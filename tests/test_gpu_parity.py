@@ -256,10 +256,19 @@ def test_cpp_host_mirror(golden, tmp_path):
     out = subprocess.run([exe, k["message_ascii"], k["sk"]["hex"], k["r"]["hex"]], capture_output=True, text=True, check=True).stdout.split("\n")
     assert out[0] == "v1 %s %s 1 1" % (k["v1_c"]["hex"], k["v1_s"]["hex"])
     assert out[1] == "v2 %s %s 1 0" % (k["v2_c"]["hex"], k["v2_s"]["hex"])
-    assert out[2] == "tampered 0" and out[3] == "zero-sk rejected" and out[4] == "batch 1000"
-    assert out[5] == "ark v1 %s %s 1 0" % (k["v1_c"]["hex"], k["v1_s"]["hex"])      # rust-arkworks/src/tests.rs:281-299
-    assert out[6] == "ark v2 %s %s 1 0" % (k["v2_c"]["hex"], k["v2_s"]["hex"])
-    assert out[7] == "identity-pk rejected"
+    # the serde-JSON writer of the C++ mirror produces the same text as the Python mirror's (and reads back there)
+    class Mock:
+        def fill_bytes(self, buf):
+            buf[:] = bytes.fromhex(k["r"]["hex"])
+    sk = plume_b200.SecretKey.from_bytes(bytes.fromhex(k["sk"]["hex"]))
+    msg = k["message_ascii"].encode()
+    assert out[2] == "json1 " + plume_b200.PlumeSignature.sign_v1(sk, msg, Mock()).to_json()
+    assert out[3] == "json2 " + plume_b200.PlumeSignature.sign_v2(sk, msg, Mock()).to_json()
+    assert plume_b200.PlumeSignature.from_json(out[2][6:]).verify()
+    assert out[4] == "tampered 0" and out[5] == "zero-sk rejected" and out[6] == "batch 1000"
+    assert out[7] == "ark v1 %s %s 1 0" % (k["v1_c"]["hex"], k["v1_s"]["hex"])      # rust-arkworks/src/tests.rs:281-299
+    assert out[8] == "ark v2 %s %s 1 0" % (k["v2_c"]["hex"], k["v2_s"]["hex"])
+    assert out[9] == "identity-pk rejected"
 
 
 def test_sec1_compressed_api(gpu_ctx):

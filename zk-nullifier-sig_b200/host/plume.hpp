@@ -130,6 +130,23 @@ struct PlumeSignature {
                   "plume_verify_batch");
         return ok != 0;
     }
+    // The serde_json form of the derive at rust-k256/src/lib.rs:66,83 (field encodings per k256 0.13: upper-case hex of the
+    // SEC1 compressed point / of the 32 scalar bytes; message as an array of numbers; unpinned by the reference -- the same
+    // text as the Python mirror's PlumeSignature.to_json, which tests/ compare).
+    std::string to_json() const {
+        auto hexu = [](const uint8_t* p, size_t n) { static const char* d = "0123456789ABCDEF"; std::string o; for (size_t i = 0; i < n; i++) { o += d[p[i] >> 4]; o += d[p[i] & 15]; } return o; };
+        auto pt = [&](const AffinePoint& a) {
+            if (a.is_identity()) return std::string("00");
+            uint8_t e[33]; e[0] = (uint8_t)(2 + (a.xy[63] & 1)); std::memcpy(e + 1, a.xy.data(), 32);
+            return hexu(e, 33);
+        };
+        std::string o = "{\"message\":[";
+        for (size_t i = 0; i < message.size(); i++) { if (i) o += ","; o += std::to_string((unsigned)message[i]); }
+        o += "],\"pk\":\"" + pt(pk) + "\",\"nullifier\":\"" + pt(nullifier) + "\",\"c\":\"" + hexu(c.data(), 32) + "\",\"s\":\"" + hexu(s.data(), 32) + "\",\"v1specific\":";
+        if (v1specific) o += "{\"r_point\":\"" + pt(v1specific->r_point) + "\",\"hashed_to_curve_r\":\"" + pt(v1specific->hashed_to_curve_r) + "\"}";
+        else o += "null";
+        return o + "}";
+    }
     template <class Rng> static PlumeSignature sign_v1(const SecretKey& sk, const std::vector<uint8_t>& msg, Rng& rng, std::shared_ptr<Context> cx = nullptr);
     template <class Rng> static PlumeSignature sign_v2(const SecretKey& sk, const std::vector<uint8_t>& msg, Rng& rng, std::shared_ptr<Context> cx = nullptr);
 };
