@@ -66,8 +66,9 @@ class Context {
     Context& operator=(const Context&) = delete;
     plume_ctx* get() const { return h_; }
     void check(int rc, const char* what) const { if (rc != PLUME_OK) throw Error(std::string(what) + ": " + plume_last_error(h_)); }
+    // the context of the single-signature calls: small generator table (16-bit windows, 64 MiB), workspaces grow on demand
     static std::shared_ptr<Context> global() {
-        static std::shared_ptr<Context> g = std::make_shared<Context>(0);
+        static std::shared_ptr<Context> g = std::make_shared<Context>(0, 16);
         return g;
     }
   private:

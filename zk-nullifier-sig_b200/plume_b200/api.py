@@ -362,9 +362,12 @@ _default_ctx = None
 
 
 def default_context():
+    """The context behind the single-signature calls (sign_v1 / sign_v2 / verify / hash_to_curve without an explicit ctx).
+    Latency, not throughput, matters there, so it takes the small generator table (16-bit windows: 64 MiB, built in
+    milliseconds) instead of the 3.2 GB one of a batch context; its workspaces grow with the batches it actually sees."""
     global _default_ctx
     if _default_ctx is None:
-        _default_ctx = PlumeContext(0)
+        _default_ctx = PlumeContext(0, fixed_window_bits=16)
     return _default_ctx
 
 
