@@ -140,6 +140,12 @@ int plume_verify_batch(plume_ctx* ctx, int version, size_t n,
 int plume_hash_to_curve_batch(plume_ctx* ctx, size_t n,
                               const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
                               uint8_t* out);
+/* The reference's own call shape, utils::hash_to_curve(m, pk) (rust-k256/src/utils.rs:11-20): the
+ * messages and the SEC1-compressed public keys as separate arrays, the library hashes m_i || pk33_i.  pk33: n x 33 slots
+ * (02/03 || x; 00 followed by zeros stands for the identity and contributes its one-byte encoding, as encode_pt does). */
+int plume_hash_to_curve_pk_batch(plume_ctx* ctx, size_t n,
+                                 const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                                 const uint8_t* pk33, uint8_t* out);
 
 /*
  * SEC1-compressed wire form: 33-byte slots, `02/03 || x` for a finite point (what

@@ -185,7 +185,7 @@ int hs_verify_batch(int flavour, int version, uint32_t n, const uint8_t* msgs, c
 
 int hs_h2c_batch(uint32_t n, const uint8_t* msgs, const uint64_t* offs, uint32_t msg_len, uint8_t* out, uint32_t binv_threads) {
     std::vector<uint32_t> ws((size_t)WS_SLOTS * n * 8);
-    h2c_args a;
+    h2c_args a{};
     a.n = n; a.msgs.base = msgs; a.msgs.offs = offs; a.msgs.fixed_len = msg_len; a.out = out; a.ws = ws.data();
     for (uint32_t i = 0; i < n; i++) h2c_stage_map(i, a);
     run_binv(a.ws, n, n, binv_threads);

@@ -260,3 +260,26 @@ def test_small_batch_latency(gpu_ctx):
         assert ok.all()
         assert min(ts) < 1.7e-3, "sign latency n=%d: %.3f ms" % (n, min(ts) * 1e3)
         assert min(tv) < 1.8e-3, "verify latency n=%d: %.3f ms" % (n, min(tv) * 1e3)
+
+
+def test_hash_to_curve_pk_batch(gpu_ctx, golden):
+    """utils::hash_to_curve(m, pk) in the reference's own call shape (rust-k256/src/utils.rs:11-20): messages and SEC1
+    public keys as separate arrays.  Equals hashing the concatenation; pins h of the reference's fixed vector; an identity
+    slot contributes the single byte 00 (encode_pt)."""
+    import c_oracle
+    import plume_b200
+    rnd = random.Random(31)
+    rng = np.random.default_rng(31)
+    n = 700
+    msgs = [bytes(rnd.randrange(256) for _ in range(rnd.choice([0, 5, 29, 32, 32, 32, 64, 200]))) for _ in range(n)]
+    pk64 = gpu_ctx.fixed_base_mul_batch(_scalars(rng, n))
+    pk33 = gpu_ctx.points_compress(pk64)
+    pk33[7] = 0                                            # the identity slot
+    got = gpu_ctx.hash_to_curve_pk_batch(msgs, pk33)
+    cat = [m + (b"\x00" if i == 7 else bytes(pk33[i])) for i, m in enumerate(msgs)]
+    assert np.array_equal(got, c_oracle.h2c_batch(cat, threads=os.cpu_count() or 1))
+    k = golden["sign_kat"]
+    inter = golden["intermediates"]
+    pk = (int(inter["pk"]["x"], 16), int(inter["pk"]["y"], 16))
+    h = plume_b200.hash_to_curve(k["message_ascii"].encode(), pk, ctx=gpu_ctx)
+    assert h == (int(inter["h"]["x"], 16), int(inter["h"]["y"], 16))

@@ -792,7 +792,7 @@ int plume_hash_to_curve_batch_device(plume_ctx* ctx, size_t n, const uint8_t* ms
     if (!out) return fail(ctx, PLUME_E_ARG, "null array");
     ScopedDevice sd(ctx->device);
     return dev_run(ctx, n, (cudaStream_t)stream, [&](size_t f, size_t k, uint32_t* ws, uint32_t*, cudaStream_t s) -> int {
-        h2c_args a;
+        h2c_args a{};
         a.n = (uint32_t)k;
         a.msgs.base = msgs_at(msgs, msg_offsets, msg_len, f); a.msgs.offs = offs_at(msg_offsets, f); a.msgs.fixed_len = (uint32_t)msg_len;
         a.out = at(out, f, 64); a.ws = ws;
@@ -923,28 +923,46 @@ int plume_ark_verify_batch(plume_ctx* ctx, int version, size_t n, const uint8_t*
                        r_point, hashed_to_curve_r, ok);
 }
 
-int plume_hash_to_curve_batch(plume_ctx* ctx, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
-                              uint8_t* out) {
+}  // extern "C" (reopened below)
+namespace {
+int h2c_host(plume_ctx* ctx, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len, const uint8_t* pk33, uint8_t* out) {
     if (!ctx) return PLUME_E_ARG;
     if (ctx_is_multi(ctx))
         return multi_split(ctx, n, [&](plume_ctx* sub, size_t f, size_t k) {
-            return plume_hash_to_curve_batch(sub, k, msgs_at(msgs, msg_offsets, msg_len, f), offs_at(msg_offsets, f), msg_len, at(out, f, 64));
+            return h2c_host(sub, k, msgs_at(msgs, msg_offsets, msg_len, f), offs_at(msg_offsets, f), msg_len, at(pk33, f, 33), at(out, f, 64));
         });
     if (int rc = check_common(ctx, n, msgs, msg_offsets, msg_len, true)) return rc;
     if (n == 0) return PLUME_OK;
     if (!out) return fail(ctx, PLUME_E_ARG, "null array");
     return run_chunks(ctx, n, 0, [&](Lane& L, size_t i0, size_t cn) -> int {
         if (int rc = lane_workspace(ctx, L, cn)) return rc;
-        if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * 64 + 4096)) return rc;
-        h2c_args a;
+        if (int rc = lane_reserve(ctx, L, msgs_bytes(msg_offsets, msg_len, i0, cn) + cn * (64 + 33) + 4096)) return rc;
+        h2c_args a{};
         a.n = (uint32_t)cn;
         if (int rc = lane_msgs(ctx, L, msgs, msg_offsets, msg_len, i0, cn, &a.msgs)) return rc;
+        if (pk33) {
+            uint8_t* d_pk;
+            if (int rc = lane_input(ctx, L, pk33 + i0 * 33, cn * 33, &d_pk)) return rc;
+            a.pk33 = d_pk;
+        }
         size_t o_out;
         a.out = lane_output(L, cn * 64, &o_out);
         a.ws = L.ws;
         if (int rc = enqueue_h2c(ctx, a, L.stream)) return rc;
         return lane_fetch(ctx, L, out + i0 * 64, o_out, cn * 64);
     });
+}
+}  // namespace
+extern "C" {
+
+int plume_hash_to_curve_batch(plume_ctx* ctx, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                              uint8_t* out) {
+    return h2c_host(ctx, n, msgs, msg_offsets, msg_len, nullptr, out);
+}
+int plume_hash_to_curve_pk_batch(plume_ctx* ctx, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
+                                 const uint8_t* pk33, uint8_t* out) {
+    if (ctx && !pk33 && n) return fail(ctx, PLUME_E_ARG, "pk33 is null");
+    return h2c_host(ctx, n, msgs, msg_offsets, msg_len, pk33, out);
 }
 
 int plume_hash_to_curve_witness_batch(plume_ctx* ctx, size_t n, const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,

@@ -647,14 +647,23 @@ PLUME_DEV void verify_stage_final(uint32_t i, const verify_args& a) {
 // ---- hash_to_curve only (rust-k256/src/utils.rs:11-20 with the preimage supplied by the caller) ----------
 struct h2c_args {
     uint32_t n;
-    msg_view msgs;            // the full preimage (PLUME: m || enc33(pk))
+    msg_view msgs;            // the full preimage (PLUME: m || enc33(pk)), or just m when pk33 is given
+    const uint8_t* pk33;      // null, or n x 33 SEC1 slots appended to the messages (00 + zeros = the identity's one byte)
     uint8_t* out;             // n x 64 affine (zeros = identity)
     uint32_t* ws;
 };
 PLUME_DEV void h2c_stage_map(uint32_t i, const h2c_args& a) {
     uint32_t len;
     const uint8_t* m = msg_ptr(a.msgs, i, len);
-    jac h = h2c_hash_to_curve(m, len, m, 0);
+    jac h;
+    if (a.pk33) {   // utils::hash_to_curve(m, pk): the preimage is m || encode_pt(pk)  (rust-k256/src/utils.rs:11-20)
+        uint8_t e[33];
+#pragma unroll 1
+        for (int k = 0; k < 33; k++) e[k] = a.pk33[(size_t)i * 33 + k];
+        h = h2c_hash_to_curve(m, len, e, e[0] == 0 ? 1u : 33u);
+    } else {
+        h = h2c_hash_to_curve(m, len, m, 0);
+    }
     ws_store_jac(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i, h);
 }
 PLUME_DEV void h2c_stage_out(uint32_t i, const h2c_args& a) {

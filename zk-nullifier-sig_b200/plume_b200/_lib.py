@@ -25,6 +25,7 @@ SYMBOLS = {
     "plume_verify_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, _u8p, _u8p, ctypes.c_size_t,
                                           _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p]),
     "plume_hash_to_curve_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, _u8p, _u8p, ctypes.c_size_t, _u8p]),
+    "plume_hash_to_curve_pk_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, _u8p, _u8p, ctypes.c_size_t, _u8p, _u8p]),
     "plume_hash_to_curve_witness_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, _u8p, _u8p, ctypes.c_size_t,
                                                          _u8p, _u8p, _u8p, _u8p, _u8p]),
     "plume_fixed_base_mul_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, _u8p, _u8p]),

@@ -350,6 +350,15 @@ class PlumeContext:
         rc = self._lib.plume_hash_to_curve_batch(self._h, n, vp(msgs), vp(msg_offsets or None), msg_len, vp(out))
         self._check(rc, "plume_hash_to_curve_batch")
 
+    def hash_to_curve_pk_batch(self, msgs, pk33):
+        """plume_hash_to_curve_pk_batch: h_i = hash_to_curve(m_i, pk_i) with pk as 33-byte SEC1 slots (utils.rs:11-20)."""
+        blob, offs, mlen, n = self._msgs(msgs, None)
+        pk = _as_u8(pk33, (n, 33))
+        o = np.empty((n, 64), dtype=np.uint8)
+        rc = self._lib.plume_hash_to_curve_pk_batch(self._h, n, _ptr(blob), _ptr(offs), mlen, _ptr(pk), _ptr(o))
+        self._check(rc, "plume_hash_to_curve_pk_batch")
+        return o
+
     def hash_to_curve_batch(self, msgs, out=None):
         blob, offs, mlen, n = self._msgs(msgs, None)
         o = out if out is not None else np.empty((n, 64), dtype=np.uint8)
@@ -606,4 +615,5 @@ class PlumeSignature:
 def hash_to_curve(m, pk, ctx=None):
     """rust-k256/src/utils.rs:11-20"""
     ctx = ctx or default_context()
-    return point_from_bytes(ctx.hash_to_curve_batch([bytes(m) + encode_pt(pk)])[0])
+    slot = encode_pt(pk).ljust(33, b"\x00")
+    return point_from_bytes(ctx.hash_to_curve_pk_batch([bytes(m)], slot)[0])

@@ -38,6 +38,9 @@ extern "C" {
     pub fn plume_hash_to_curve_batch(
         ctx: *mut plume_ctx, n: usize, msgs: *const u8, msg_offsets: *const u64, msg_len: usize, out: *mut u8,
     ) -> c_int;
+    pub fn plume_hash_to_curve_pk_batch(
+        ctx: *mut plume_ctx, n: usize, msgs: *const u8, msg_offsets: *const u64, msg_len: usize, pk33: *const u8, out: *mut u8,
+    ) -> c_int;
     pub fn plume_sign_batch_device(
         ctx: *mut plume_ctx, version: c_int, n: usize, msgs: *const u8, msg_offsets: *const u64, msg_len: usize,
         sk: *const u8, r: *const u8, pk: *mut u8, nullifier: *mut u8, c: *mut u8, s: *mut u8,
