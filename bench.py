@@ -557,13 +557,18 @@ def run_leg(env, workload, lg, steps, warmup, with_cpu_baseline=False, with_page
     per_launch_items = min(chunk, n)
     avg_ms = stage[dom]["ms_total"] / stage[dom]["launches"]
     kind = dom if dom in WORK_MS else "h2c_map"
+    if dom in ("sign_varbase", "sign_tab") and "sign_tab" in stage and "sign_varbase" in stage:
+        # the signer's h^r, h^sk is two kernels (comb table, comb ladders) with ONE algorithmic count: they are rated together
+        avg_ms = sum(stage[k]["ms_total"] / stage[k]["launches"] for k in ("sign_tab", "sign_varbase"))
+        dom, kind = "sign_tab+sign_varbase", "sign_varbase"
     ach = per_launch_items * work_lp(kind) / (avg_ms * 1e-3)
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full summary
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
-        if dom in tj:   # per item, scaled to this launch (the kernel's traffic is proportional to the items)
-            traffic = tj[dom]["dram_bytes_per_launch"] * per_launch_items / tj[dom]["items_per_launch"]
+        parts = ("sign_tab", "sign_varbase") if dom.startswith("sign_tab+") else (dom,)
+        if all(k in tj for k in parts):   # per item, scaled to this launch (the kernel's traffic is proportional to the items)
+            traffic = sum(tj[k]["dram_bytes_per_launch"] * per_launch_items / tj[k]["items_per_launch"] for k in parts)
     except Exception:
         pass
     rec["roofline"] = {"bound": "int-alu", "kernel": dom, "achieved": ach, "peak": peak_lp, "unit": "limb-products/s",
@@ -594,7 +599,7 @@ def run_leg(env, workload, lg, steps, warmup, with_cpu_baseline=False, with_page
             per_kernel[label] = {"ms": round(t, 3), "frac": round(per_launch_items * work_lp(st_kind) / (t * 1e-3) / peak_lp, 4)}
     rec["roofline"]["per_kernel"] = per_kernel
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    gbs = per_launch_items * BYTES.get(dom, 160) / (avg_ms * 1e-3) / 1e9
+    gbs = per_launch_items * BYTES.get(kind if dom.startswith("sign_tab+") else dom, 160) / (avg_ms * 1e-3) / 1e9
     rec["roofline"]["hbm"] = {"achieved_gbs": gbs, "peak_gbs": hbm_peak, "frac": gbs / hbm_peak,
                               "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}
     # whole-step view: all kernels of the step against the same peak
