@@ -77,9 +77,15 @@ def work_lp(kind, survey_units=False):
     return (m + sq) * LP_PER_M if survey_units else m * LP_PER_M + sq * LP_PER_S
 
 
-# algorithmic bytes per item of the dominant kernels (what they must read + write in HBM)
-BYTES = {"sign_varbase": 3 * 32 + 64 + 2 * 32 + 6 * 32, "verify_muls": 3 * 32 + 64 * 2 + 64 + 2 * 32 + 6 * 32,
-         "verify_mul_a": 64 + 2 * 32 + 3 * 32, "verify_mul_b": 2 * 32 + 32 + 3 * 32, "verify_tab_b": 3 * 32 + 64 + 3 * 32}
+# algorithmic bytes per item of the big kernels: what each must move through HBM given the stage split -- its inputs and outputs
+# (32-byte scalars / coordinates, 64-byte points, 32-byte workspace slots) plus, ONCE, the per-item table that travels from a
+# table kernel to its ladder kernel through HBM (16 or 2 x 8 entries of 128 bytes = 2 KiB).  Tables a kernel builds and walks
+# itself (verify_mul_a's) and re-reads of entries are not algorithmic; the measured traffic (profiles/traffic.json) exceeds
+# these figures by 2-7 x because ~110 000 resident threads x 2-4 KiB of table do not fit the 126 MB L2.
+BYTES = {"sign_tab": 3 * 32 + 2048 + 2 * 32, "sign_varbase": 2048 + 2 * 32 + 2 * 32 + 6 * 32,
+         "sign_tab+sign_varbase": 3 * 32 + 2 * 2048 + 2 * 32 + 6 * 32,
+         "verify_mul_a": 64 + 2 * 32 + 12 * 64 + 3 * 32, "verify_mul_b": 2048 + 2 * 32 + 2 * 32 + 3 * 32,
+         "verify_tab_b": 3 * 32 + 64 + 2048 + 2 * 32, "h2c_map": 65 + 3 * 32, "sign_h2c": 32 + 6 * 32 + 3 * 32, "verify_h2c": 32 + 64 * 4 + 64 + 3 * 32}
 
 
 _K256 = np.array([
@@ -599,8 +605,10 @@ def run_leg(env, workload, lg, steps, warmup, with_cpu_baseline=False, with_page
             per_kernel[label] = {"ms": round(t, 3), "frac": round(per_launch_items * work_lp(st_kind) / (t * 1e-3) / peak_lp, 4)}
     rec["roofline"]["per_kernel"] = per_kernel
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    gbs = per_launch_items * BYTES.get(kind if dom.startswith("sign_tab+") else dom, 160) / (avg_ms * 1e-3) / 1e9
+    alg_bytes = per_launch_items * BYTES.get(dom, 160)
+    gbs = alg_bytes / (avg_ms * 1e-3) / 1e9
     rec["roofline"]["hbm"] = {"achieved_gbs": gbs, "peak_gbs": hbm_peak, "frac": gbs / hbm_peak,
+                              "algorithmic_bytes": alg_bytes, "traffic_over_algorithmic": (traffic / alg_bytes) if traffic else None,
                               "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}
     # whole-step view: all kernels of the step against the same peak
     kinds = {"sign_verify": ("sign", "verify"), "config4": ("sign", "verify"), "sign": ("sign",), "verify": ("verify",),

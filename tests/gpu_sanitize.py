@@ -30,7 +30,8 @@ assert np.array_equal(w["h"], h)
 ctx.registers_batch(o["c"])
 c33 = ctx.points_compress(o["pk"])
 ctx.points_decompress(c33)
-ctx.fixed_base_mul_batch(sk)
+pts = ctx.fixed_base_mul_batch(sk)
+ctx.hash_to_curve_pk_batch(msgs, ctx.points_compress(pts))
 # fixed 32-byte and 65-byte records (the fixed-layout b0 path, word and byte loads), and a batch above the small-batch
 # threshold (no second stream) next to the ones above (second stream for G*s - pk*c)
 fixed = rng.integers(0, 256, (n, 32), dtype=np.uint8)
