@@ -23,9 +23,17 @@ pub struct Engine(*mut ffi::plume_ctx);
 unsafe impl Send for Engine {}
 
 impl Engine {
-    pub fn new(device: i32) -> Result<Self, String> {
+    /// One context over `devices` (one entry: a single-device context; several: the batch calls range-split
+    /// over them inside the library).  `window_bits` 0 = the library's default generator table (22 bits, 2 GiB).
+    pub fn new(devices: &[i32], window_bits: i32) -> Result<Self, String> {
         let mut h = core::ptr::null_mut();
-        let rc = unsafe { ffi::plume_ctx_create(&mut h, device, 0) };
+        let rc = unsafe {
+            if devices.len() == 1 {
+                ffi::plume_ctx_create(&mut h, devices[0], window_bits)
+            } else {
+                ffi::plume_ctx_create_multi(&mut h, devices.as_ptr(), devices.len() as i32, window_bits)
+            }
+        };
         if rc != ffi::PLUME_OK {
             let msg = unsafe { std::ffi::CStr::from_ptr(ffi::plume_last_error(core::ptr::null())) };
             return Err(msg.to_string_lossy().into_owned());
@@ -38,9 +46,18 @@ impl Drop for Engine {
         unsafe { ffi::plume_ctx_destroy(self.0) }
     }
 }
+/// The process-wide engine behind the reference-shaped calls: GPUs from `PLUME_DEVICES` ("0,1,2,3"; default "0"),
+/// a 16-bit generator table (32 MiB, built in milliseconds) unless `PLUME_FIXED_WINDOW` says otherwise.
 fn engine() -> &'static Mutex<Engine> {
     static E: OnceLock<Mutex<Engine>> = OnceLock::new();
-    E.get_or_init(|| Mutex::new(Engine::new(0).expect("no B200 / libplume_b200 available (there is no CPU fallback)")))
+    E.get_or_init(|| {
+        let devices: Vec<i32> = std::env::var("PLUME_DEVICES").ok()
+            .map(|v| v.split(',').filter_map(|t| t.trim().parse().ok()).collect())
+            .filter(|v: &Vec<i32>| !v.is_empty())
+            .unwrap_or_else(|| vec![0]);
+        let window = if std::env::var_os("PLUME_FIXED_WINDOW").is_some() { 0 } else { 16 };
+        Mutex::new(Engine::new(&devices, window).expect("no B200 / libplume_b200 available (there is no CPU fallback)"))
+    })
 }
 
 fn point_to_wire(p: &KAffine) -> [u8; 64] {
