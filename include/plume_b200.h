@@ -56,6 +56,7 @@ extern "C" {
 #define PLUME_E_NO_DEVICE (-2)  /* no CUDA device / device index out of range */
 #define PLUME_E_CUDA (-3)       /* CUDA runtime error, see plume_last_error */
 #define PLUME_E_NOMEM (-4)      /* allocation failed */
+#define PLUME_E_SELFTEST (-5)   /* plume_self_test: a result differs from the reference's vectors, see plume_last_error */
 
 /* per-item status of plume_sign_batch: the places where the reference panics
  * (rust-k256/src/randomizedsigner.rs:61, :91, :95) or rejects its inputs */
@@ -89,6 +90,13 @@ void plume_ctx_destroy(plume_ctx* ctx);
  * table concurrently unless PLUME_GTAB_BCAST=p2p|nccl asks for device 0's table to be broadcast (peer copies over
  * NVLink / ncclBroadcast; measured, not faster: DESIGN.md section 6). */
 int plume_ctx_create_multi(plume_ctx** out, const int* devices, int n_devices, int fixed_window_bits);
+/* Known-answer test of the context through its own batch calls: the reference's signing vector (rust-k256/tests/signing.rs:9-21:
+ * message, sk, mock-RNG nonce -> V1 and V2 c, s), its intermediate points (rust-arkworks/src/tests.rs:191-262: pk, g^r, h, h^r,
+ * nullifier) and hash_to_curve("abc") (rust-k256/tests/verification.rs:288-292), 300 copies per batch so that more than one
+ * warp and block take part, one tampered copy that verification has to reject.  A few milliseconds; every device of a
+ * multi-device context runs it.  PLUME_OK, PLUME_E_SELFTEST (plume_last_error names the field) or the error of the failing call.
+ * Meant for a binding's start-up path: the product has no CPU implementation to compare itself with. */
+int plume_self_test(plume_ctx* ctx);
 int plume_ctx_device_count(const plume_ctx* ctx);          /* 1 for a single-device context */
 /* The range split itself (no device needed): part `part` of `parts` owns items [first, first + count) of n. */
 int plume_shard_range(size_t n, int part, int parts, size_t* first, size_t* count);

@@ -283,3 +283,15 @@ def test_hash_to_curve_pk_batch(gpu_ctx, golden):
     pk = (int(inter["pk"]["x"], 16), int(inter["pk"]["y"], 16))
     h = plume_b200.hash_to_curve(k["message_ascii"].encode(), pk, ctx=gpu_ctx)
     assert h == (int(inter["h"]["x"], 16), int(inter["h"]["y"], 16))
+
+
+def test_library_self_test(gpu_ctx):
+    """plume_self_test: the reference's vectors (rust-k256/tests/signing.rs:9-21, rust-arkworks/src/tests.rs:191-262,
+    rust-k256/tests/verification.rs:288-292) through the context's own calls, single- and multi-device."""
+    import plume_b200
+    from plume_b200 import _lib
+    gpu_ctx.self_test()
+    with plume_b200.PlumeContext(_device_list()[:2], fixed_window_bits=12) as ctx:
+        ctx.self_test()
+    # a null context is an argument error, not a crash
+    assert _lib.load().plume_self_test(None) == -1

@@ -66,9 +66,12 @@ class Context {
     Context& operator=(const Context&) = delete;
     plume_ctx* get() const { return h_; }
     void check(int rc, const char* what) const { if (rc != PLUME_OK) throw Error(std::string(what) + ": " + plume_last_error(h_)); }
-    // the context of the single-signature calls: small generator table (16-bit windows, 64 MiB), workspaces grow on demand
+    // the reference's known-answer vectors through this context (plume_self_test); throws naming the field that differs
+    void self_test() const { check(plume_self_test(h_), "plume_self_test"); }
+    // the context of the single-signature calls: small generator table (16-bit windows, 64 MiB), workspaces grow on demand;
+    // self-tested once when it is created
     static std::shared_ptr<Context> global() {
-        static std::shared_ptr<Context> g = std::make_shared<Context>(0, 16);
+        static std::shared_ptr<Context> g = [] { auto c = std::make_shared<Context>(0, 16); c->self_test(); return c; }();
         return g;
     }
   private:

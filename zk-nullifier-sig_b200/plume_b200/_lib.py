@@ -29,6 +29,7 @@ SYMBOLS = {
     "plume_hash_to_curve_witness_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, _u8p, _u8p, ctypes.c_size_t,
                                                          _u8p, _u8p, _u8p, _u8p, _u8p]),
     "plume_fixed_base_mul_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, _u8p, _u8p]),
+    "plume_self_test": (ctypes.c_int, [ctypes.c_void_p]),
     "plume_debug_read_arena": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u8p, _u8p, ctypes.c_size_t,
                                               ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]),
     "plume_registers_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, _u8p, _u8p]),

@@ -111,6 +111,11 @@ class PlumeContext:
         if rc != 0:
             raise PlumeError("%s failed (%d): %s" % (what, rc, self._lib.plume_last_error(self._h).decode()))
 
+    def self_test(self):
+        """plume_self_test: the reference's known-answer vectors through this context's own batch calls (every device of a
+        multi-device context); raises PlumeError naming the field that differs."""
+        self._check(self._lib.plume_self_test(self._h), "plume_self_test")
+
     @property
     def chunk_items(self):
         return self._lib.plume_ctx_chunk_items(self._h)
@@ -376,7 +381,9 @@ def default_context():
     milliseconds) instead of the 3.2 GB one of a batch context; its workspaces grow with the batches it actually sees."""
     global _default_ctx
     if _default_ctx is None:
-        _default_ctx = PlumeContext(0, fixed_window_bits=16)
+        ctx = PlumeContext(0, fixed_window_bits=16)
+        ctx.self_test()          # once per process: a GPU / driver / build that disagrees with the reference's vectors stops here
+        _default_ctx = ctx
     return _default_ctx
 
 

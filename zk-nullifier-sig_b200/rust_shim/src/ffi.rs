@@ -63,6 +63,7 @@ extern "C" {
         ctx: *mut plume_ctx, n: usize, msgs: *const u8, msg_offsets: *const u64, msg_len: usize,
         u: *mut u8, q: *mut u8, gx1_square: *mut u8, h: *mut u8, hints: *mut u8,
     ) -> c_int;
+    pub fn plume_self_test(ctx: *mut plume_ctx) -> c_int;
     pub fn plume_fixed_base_mul_batch(ctx: *mut plume_ctx, n: usize, scalars: *const u8, out: *mut u8) -> c_int;
     pub fn plume_registers_batch(ctx: *mut plume_ctx, n: usize, in32: *const u8, out4: *mut u64) -> c_int;
 }

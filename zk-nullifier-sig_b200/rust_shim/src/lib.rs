@@ -56,7 +56,13 @@ fn engine() -> &'static Mutex<Engine> {
             .filter(|v: &Vec<i32>| !v.is_empty())
             .unwrap_or_else(|| vec![0]);
         let window = if std::env::var_os("PLUME_FIXED_WINDOW").is_some() { 0 } else { 16 };
-        Mutex::new(Engine::new(&devices, window).expect("no B200 / libplume_b200 available (there is no CPU fallback)"))
+        let eng = Engine::new(&devices, window).expect("no B200 / libplume_b200 available (there is no CPU fallback)");
+        // the reference's known-answer vectors on every device, once per process
+        if unsafe { ffi::plume_self_test(eng.0) } != ffi::PLUME_OK {
+            let msg = unsafe { std::ffi::CStr::from_ptr(ffi::plume_last_error(eng.0)) };
+            panic!("libplume_b200 self test failed: {}", msg.to_string_lossy());
+        }
+        Mutex::new(eng)
     })
 }
 
