@@ -55,3 +55,24 @@ def test_sm100a_sass_present():
         pytest.skip("cuobjdump not available")
     out = subprocess.run([cuobjdump, "-lelf", plume_b200.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_self_test_vectors_are_the_golden_ones():
+    """The constants plume_self_test compares against (csrc/selftest.cu) are the reference's vectors of
+    tests/golden/reference_vectors.json, so a typo there cannot hide behind a GPU-only test."""
+    import json
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_vectors.json")))
+    src = open(os.path.join(ROOT, "zk-nullifier-sig_b200", "csrc", "selftest.cu")).read()
+    body = src[src.index("struct Kat {"):src.index("\n};", src.index("struct Kat {"))]
+    fields = {}
+    for name, val in re.findall(r"const char\* (\w+)(?:\[2\])? = (.*?);", body, flags=re.S):
+        fields[name] = ["".join(re.findall(r'"([^"]*)"', part)) for part in (val.strip("{} \n").split(",") if val.lstrip().startswith("{") else [val])]
+    kat, mid = g["sign_kat"], g["intermediates"]
+    xy = lambda p: p["x"] + p["y"]
+    assert fields["msg"] == [kat["message_ascii"]]
+    assert fields["sk"] == [kat["sk"]["hex"]] and fields["r"] == [kat["r"]["hex"]]
+    assert fields["c"] == [kat["v1_c"]["hex"], kat["v2_c"]["hex"]]
+    assert fields["s"] == [kat["v1_s"]["hex"], kat["v2_s"]["hex"]]
+    assert fields["pk"] == [xy(mid["pk"])] and fields["g_r"] == [xy(mid["g_r"])]
+    assert fields["h"] == [xy(mid["h"])] and fields["h_r"] == [xy(mid["h_r"])] and fields["h_sk"] == [xy(mid["h_sk"])]
+    assert fields["h2c_abc"] == [xy(g["h2c_abc"])]
