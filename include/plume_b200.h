@@ -284,7 +284,7 @@ int plume_measure_imad_rates(plume_ctx* ctx, int iters, double* plain_limb_produ
 
 /* Test hook: element-wise base-field operation on raw limb arrays (n x 8 little-endian 32-bit limbs,
  * any representative below 2^256; host pointers).  op: 0 a*b, 1 a^2, 2 a+b, 3 a-b, 4 1/a, 5 canonical(a),
- * 6 a*b[0] (small), 7 a^((p-3)/4), 8 -a, 9 a^((p+1)/4), 10 a == 0 (mod p), 11 8a, 12 2a, 13 4a.  Results are weakly reduced
+ * 6 a*b[0] (small), 7 a^((p-3)/4), 8 -a, 9 a^((p+1)/4), 10 a == 0 (mod p), 11 8a, 12 2a, 13 4a, 14 1/a by division steps (0 for 0).  Results are weakly reduced
  * (compare modulo p).  Exists so that the carry-chain assembly of the field layer can be checked in
  * isolation on the GPU (tests/test_gpu_field.py); not part of the reference's interface. */
 int plume_debug_fe_op(plume_ctx* ctx, int op, size_t n, const uint32_t* a, const uint32_t* b, uint32_t* out);

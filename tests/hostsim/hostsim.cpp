@@ -44,6 +44,7 @@ void hs_fe_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
         case 2: r = fe_add(x, y); break;
         case 3: r = fe_sub(x, y); break;
         case 4: r = fe_inv(x); break;
+        case 14: r = fe_inv_var(x); break;
         case 5: r = fe_norm(x); break;
         case 6: r = fe_mul_small(x, b[0]); break;
         case 7: r = fe_pow_pm3d4(x); break;
@@ -117,6 +118,43 @@ void hs_fb_mul(const uint8_t* k32, int w, uint8_t* out64) {
     jac r = fb_mul(k, g_tab.data(), w);
     aff q = r.inf ? aff_infinity() : aff_from_jac_zinv(r, fe_inv(r.z));
     st_point_be(out64, q);
+}
+
+// The per-lane shares of the small-batch ("team") kernels, added up serially here: the two GLV halves of the windowed
+// ladder / of the signed comb, and the lower and upper windows of the generator walk.
+static void hs_store(const jac& r, uint8_t* out64) {
+    aff q = r.inf ? aff_infinity() : aff_from_jac_zinv(r, fe_inv(r.z));
+    st_point_be(out64, q);
+}
+void hs_vb_mul_halves(const uint8_t* p64, const uint8_t* k32, uint8_t* out64) {
+    aff p; ld_point_be(p, p64);
+    sc k = ld_sc_be(k32);
+    uint32_t tabw[VB_TAB_WORDS];
+    fe zg = vb_build_table(p.x, p.y, tabw, true);
+    glv_half h1, h2;
+    glv_split(k, h1, h2);
+    jac r = jac_add(vb_ladder_half(h1, false, tabw), vb_ladder_half(h2, true, tabw));
+    if (!r.inf) r.z = fe_mul(r.z, zg);
+    hs_store(r, out64);
+}
+void hs_comb_mul_halves(const uint8_t* p64, const uint8_t* k32, uint8_t* out64) {
+    aff p; ld_point_be(p, p64);
+    sc k = ld_sc_be(k32);
+    uint32_t area[COMB_AREA_WORDS];
+    fe zg = comb_build_table(p.x, p.y, area);
+    fe zg2 = fe_sqr(zg);
+    fe pxs = fe_mul(p.x, zg2), pys = fe_mul(p.y, fe_mul(zg2, zg));
+    glv_half h1, h2;
+    glv_split(k, h1, h2);
+    jac r = jac_add(comb_ladder_half(h1, false, area, pxs, pys), comb_ladder_half(h2, true, area, pxs, pys));
+    if (!r.inf) r.z = fe_mul(r.z, zg);
+    hs_store(r, out64);
+}
+void hs_fb_mul_split(const uint8_t* k32, int w, uint8_t* out64) {
+    build_gtab(w);
+    sc k = ld_sc_be(k32);
+    const int nw = fb_windows(w), mid = nw / 2;
+    hs_store(jac_add(fb_mul_windows(k, g_tab.data(), w, 0, mid), fb_mul_windows(k, g_tab.data(), w, mid, nw)), out64);
 }
 
 // flavour 0: k256 (pk is an output), 1: arkworks (pk is an input)

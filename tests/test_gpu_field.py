@@ -66,6 +66,9 @@ def test_field_ops(gpu_ctx):
     inv = _ints(gpu_ctx.debug_fe_op(4, a[:m], b[:m]))
     p34 = _ints(gpu_ctx.debug_fe_op(7, a[:m], b[:m]))
     sq = _ints(gpu_ctx.debug_fe_op(9, a[:m], b[:m]))
+    invv = _ints(gpu_ctx.debug_fe_op(14, a, b))     # the division-step inversion of the small-batch path, every value
+    for i, x in enumerate(A):
+        assert invv[i] % P == (pow(x, -1, P) if x % P else 0), ("inv_var", hex(x))
     for i, x in enumerate(A[:m]):
         if x % P:
             assert inv[i] % P == pow(x, -1, P)

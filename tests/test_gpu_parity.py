@@ -322,3 +322,53 @@ def test_sec1_compressed_api(gpu_ctx):
         assert ok[3::4].all() and not ok[0::4].any()
         if ver == 1:
             assert not ok[2::4].any()
+
+
+def test_small_batch_kernels_every_size(gpu_ctx):
+    """Batches of at most PLUME_TEAM_MAX (4 096) items run the small-batch kernels (k_team.cu: 2 or 4 lanes per item, points
+    added by shuffles).  Sizes that leave whole warps, part of a warp and part of a team's block unused, both versions, ragged
+    messages; 4 097 items is the first size back on the throughput kernels."""
+    rnd = random.Random(41)
+    rng = np.random.default_rng(41)
+    for n in (1, 2, 3, 5, 8, 31, 32, 33, 63, 64, 65, 127, 1000, 4096, 4097):
+        msgs = [bytes(rnd.randrange(256) for _ in range(rnd.choice([0, 1, 32, 33, 65, 90]))) for _ in range(n)]
+        sk, r = _rand_scalars(rng, n), _rand_scalars(rng, n)
+        if n >= 3:
+            sk[1] = 0                                        # a rejected item in the middle of a warp
+            r[n - 1] = 0xFF
+        for ver in (1, 2):
+            o = _sign_both(gpu_ctx, ver, msgs, sk, r)
+            bad = o["s"].copy()
+            if n >= 2:
+                bad[n // 2, 31] ^= 1
+            t = dict(o); t["s"] = bad
+            got = _verify_both(gpu_ctx, ver, msgs, t)
+            want = (o["status"] == 0)
+            if n >= 2:
+                want[n // 2] = False
+            assert np.array_equal(got.astype(bool), want)
+
+
+@pytest.fixture(scope="module")
+def throughput_ctx():
+    """A context with the small-batch kernels switched off: every batch, however small, on the throughput kernels."""
+    import plume_b200
+    os.environ["PLUME_TEAM_MAX"] = "0"
+    try:
+        ctx = plume_b200.PlumeContext(0, fixed_window_bits=16)
+    finally:
+        del os.environ["PLUME_TEAM_MAX"]
+    yield ctx
+    ctx.close()
+
+
+def test_small_batches_on_the_throughput_kernels(throughput_ctx):
+    """The edge cases above run small batches, i.e. the small-batch kernels; the same cases with those switched off keep the
+    throughput kernels (what a 2^20 batch runs) under the same edge-case coverage."""
+    test_ragged_messages_and_bad_scalars(throughput_ctx)
+    test_fixed_length_records(throughput_ctx)
+    test_tampered_and_malformed_verify_inputs(throughput_ctx)
+    test_identity_forgery_agrees_with_oracle(throughput_ctx)
+    import test_arkworks_flavour as A
+    A.test_gpu_ark_sign_and_verify_match_oracle(throughput_ctx)
+    throughput_ctx.self_test()

@@ -47,6 +47,20 @@ def test_field_arithmetic_limb_level():
         assert H.fe_op(9, a) % P == pow(a, (P + 1) // 4, P)
 
 
+def test_division_step_inversion():
+    """inv.cuh fe_inv_var (Bernstein-Yang division steps, 30 at a time): against pow(x, -1, p) on edge values (0 and p give 0
+    through the Fermat fallback), non-canonical representatives, powers of two, values with long runs, and random ones."""
+    rnd = random.Random(77)
+    vals = [0, P, 1, 2, 3, P - 1, P - 2, P + 1, 2**256 - 1, 2**255, 2**32 + 977, 977, 2**32, 0xFFFFFFFF, (P + 1) // 2, (P - 1) // 2,
+            2**224 - 1, (1 << 256) - (1 << 224), 0x5555555555555555555555555555555555555555555555555555555555555555 % 2**256,
+            0xAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA]
+    vals += [1 << k for k in range(0, 256, 7)] + [(1 << k) - 1 for k in range(2, 256, 11)] + [P - (1 << k) for k in range(0, 250, 13)]
+    vals += [rnd.randrange(2**256) for _ in range(1500)] + [rnd.randrange(2**64) for _ in range(50)]
+    for a in vals:
+        got = H.fe_op(14, a) % P
+        assert got == (pow(a, -1, P) if a % P else 0), hex(a)
+
+
 def test_scalar_arithmetic_and_glv():
     rnd = random.Random(2)
     sv = [0, 1, 2, N - 1, N - 2, N // 2, N // 2 + 1, 2**128, 2**129 - 1, LAMBDA, N - LAMBDA] + [rnd.randrange(N) for _ in range(100)]
@@ -119,6 +133,25 @@ def test_signed_comb_scalar_multiplication():
         out = (ctypes.c_uint8 * 64)()
         H.lib().hs_comb_mul(base, k.to_bytes(32, "big"), out)
         assert bytes(out) == (c_oracle.mul(base, k) if k else bytes(64)), hex(k)
+
+
+def test_team_shares_add_up():
+    """The per-lane shares of the small-batch kernels (stages_team.cuh): the GLV halves of the windowed ladder and of the
+    signed comb, and the two window ranges of the generator walk, summed, are k * P."""
+    rnd = random.Random(31)
+    ks = [0, 1, 2, 3, N - 1, N - 2, 2**128, 2**128 - 1, LAMBDA, LAMBDA + 1, N - LAMBDA, (LAMBDA * 2) % N, 0xFFFFFFFF, 2**255 % N]
+    ks += [rnd.randrange(N) for _ in range(16)]
+    for t, k in enumerate(ks):
+        base = c_oracle.mul_g(rnd.randrange(1, N)) if t % 3 else _pt64(R.G)
+        want = c_oracle.mul(base, k) if k else bytes(64)
+        for fn in (H.lib().hs_vb_mul_halves, H.lib().hs_comb_mul_halves):
+            out = (ctypes.c_uint8 * 64)()
+            fn(base, k.to_bytes(32, "big"), out)
+            assert bytes(out) == want, hex(k)
+        for w in (8, 11):
+            out = (ctypes.c_uint8 * 64)()
+            H.lib().hs_fb_mul_split(k.to_bytes(32, "big"), w, out)
+            assert bytes(out) == (c_oracle.mul_g(k) if k else bytes(64)), hex(k)
 
 
 def test_h2c_pipeline(golden):

@@ -92,20 +92,26 @@ int run_stage(plume_ctx* ctx, int stage, cudaStream_t s, F&& launch) {
 
 // batched inversion of m workspace elements starting at slot `slot` (WS_Z0: both Z arrays when m = 2n; WS_Z1: the second)
 int binv(plume_ctx* ctx, uint32_t* ws, uint32_t n, uint32_t m, cudaStream_t s, int slot = WS_Z0) {
-    RUN(ST_BINV, launch_binv(ws + (size_t)slot * n * 8, ws + (size_t)WS_P0 * n * 8, m, ctx->binv_k, s));
+    // small batches: short chains (4 elements per inversion) and the division-step inversion -- latency, not throughput
+    const bool small = n <= ctx->team_max;
+    RUN(ST_BINV, launch_binv(ws + (size_t)slot * n * 8, ws + (size_t)WS_P0 * n * 8, m, small ? 4u : ctx->binv_k, s, small));
     return PLUME_OK;
 }
 
+// Small batches (n <= team_max) leave the GPU almost idle with one thread per item; what the caller waits for is the
+// length of the dependent chain, so the stages that have independent parts run them on 2 or 4 neighbouring lanes
+// (k_team.cu, stages_team.cuh).  Same workspace conventions, same results.
 int enqueue_sign(plume_ctx* ctx, sign_args a, cudaStream_t s) {
-    RUN(ST_SIGN_FIXED, launch_sign_fixed(a, s));
+    const bool team = a.n <= ctx->team_max;
+    RUN(ST_SIGN_FIXED, team ? launch_sign_fixed_team(a, s) : launch_sign_fixed(a, s));
     if (int rc = binv(ctx, a.ws, a.n, 2 * a.n, s)) return rc;
-    RUN(ST_SIGN_H2C, launch_sign_h2c(a, s));
+    RUN(ST_SIGN_H2C, team ? launch_sign_h2c_team(a, s) : launch_sign_h2c(a, s));
     if (int rc = binv(ctx, a.ws, a.n, a.n, s)) return rc;
 #ifdef PLUME_SIGN_ONE_KERNEL
     RUN(ST_SIGN_VARBASE, launch_sign_varbase(a, s));
 #else
     RUN(ST_SIGN_TAB, launch_sign_comb_tab(a, s));
-    RUN(ST_SIGN_VARBASE, launch_sign_comb_lad(a, s));
+    RUN(ST_SIGN_VARBASE, team ? launch_sign_comb_lad_team(a, s) : launch_sign_comb_lad(a, s));
 #endif
     if (int rc = binv(ctx, a.ws, a.n, 2 * a.n, s)) return rc;
     RUN(ST_SIGN_FINAL, launch_sign_final(a, s));
@@ -117,21 +123,22 @@ const uint32_t kSmallBatch = 8192;
 
 int enqueue_verify(plume_ctx* ctx, verify_args a, cudaStream_t s) {
     const bool fork = a.n <= kSmallBatch && ctx->aux_stream != nullptr;
-    RUN(ST_VERIFY_H2C, launch_verify_h2c(a, s));
+    const bool team = a.n <= ctx->team_max;
+    RUN(ST_VERIFY_H2C, team ? launch_verify_h2c_team(a, s) : launch_verify_h2c(a, s));
     if (fork) {   // A needs the input checks of the first stage (ok[]) and nothing else: start it next to the stages of B
         cudaStream_t sa = ctx->aux_stream;
         CU(cudaEventRecord(ctx->ev_fork, s));
         CU(cudaStreamWaitEvent(sa, ctx->ev_fork, 0));
-        if (int rc = run_stage(ctx, ST_VERIFY_MUL_A, sa, [&]() -> cudaError_t { return launch_verify_mul_a(a, sa); })) return rc;
+        if (int rc = run_stage(ctx, ST_VERIFY_MUL_A, sa, [&]() -> cudaError_t { return team ? launch_verify_mul_a_team(a, sa) : launch_verify_mul_a(a, sa); })) return rc;
         CU(cudaEventRecord(ctx->ev_join, sa));
     }
     if (int rc = binv(ctx, a.ws, a.n, a.n, s, WS_Z1)) return rc;
     // separate kernels, each with its own register budget: one fused kernel needs 168 registers (12 warps/SM), the
     // ladders alone run at 128 or fewer (16-24 warps/SM); 18 % faster in total (round 1)
     RUN(ST_VERIFY_TAB_B, launch_verify_tab_b(a, s));
-    RUN(ST_VERIFY_MUL_B, launch_verify_lad_b(a, s));
+    RUN(ST_VERIFY_MUL_B, team ? launch_verify_lad_b_team(a, s) : launch_verify_lad_b(a, s));
     if (fork) CU(cudaStreamWaitEvent(s, ctx->ev_join, 0));
-    else RUN(ST_VERIFY_MUL_A, launch_verify_mul_a(a, s));
+    else RUN(ST_VERIFY_MUL_A, team ? launch_verify_mul_a_team(a, s) : launch_verify_mul_a(a, s));
     if (int rc = binv(ctx, a.ws, a.n, 2 * a.n, s)) return rc;
     RUN(ST_VERIFY_FINAL, launch_verify_final(a, s));
     return PLUME_OK;
@@ -500,6 +507,7 @@ int ctx_create_single(plume_ctx** out, int device, int fixed_window_bits, const 
     if (c->host_chunk > c->chunk) c->host_chunk = c->chunk;
     c->binv_k = (uint32_t)env_size("PLUME_BINV_K", 32);   // elements per inversion: 8 -> 0.42 ms per 2^21 elements, 16 -> 0.27, 32 -> 0.21, 64 -> 0.21
     c->stage_threads = (int)env_size("PLUME_STAGE_THREADS", 8);
+    if (const char* e = getenv("PLUME_TEAM_MAX")) c->team_max = (uint32_t)strtoul(e, nullptr, 10);   // 0 switches the small-batch kernels off
     { const char* v = getenv("PLUME_DEVICE_SPLIT"); c->dev_split = !(v && v[0] == '0'); }
     struct Guard { plume_ctx* c; ~Guard() { if (c) plume_ctx_destroy(c); } } guard{c};
     for (int k = 0; k < 2; k++) CU(cudaStreamCreateWithFlags(&c->lanes[k].stream, cudaStreamNonBlocking));

@@ -188,6 +188,33 @@ PLUME_DEV jac jac_add(const jac& p, const jac& q) {
 
 PLUME_DEV jac jac_neg(const jac& p) { jac r = p; r.y = fe_neg(p.y); return r; }
 
+#ifndef PLUME_HOSTSIM
+// Lane exchange for the small-batch ("team") kernels, in which the 2 or 4 neighbouring lanes of a warp that belong to one
+// item each compute a share of a sum of points.  `mask` names the warp's live lanes (whole teams; __ballot_sync at kernel
+// entry, before the lanes past the end of the batch leave).
+PLUME_DEV fe fe_shfl_xor(uint32_t mask, const fe& a, int m) {
+    fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_xor_sync(mask, a.v[i], m);
+    return r;
+}
+PLUME_DEV jac jac_shfl_xor(uint32_t mask, const jac& p, int m) {
+    jac r;
+    r.x = fe_shfl_xor(mask, p.x, m); r.y = fe_shfl_xor(mask, p.y, m); r.z = fe_shfl_xor(mask, p.z, m);
+    r.inf = __shfl_xor_sync(mask, p.inf, m);
+    return r;
+}
+// the sum of the points of a team of 2^levels lanes; `q` = the lane's index in its team.  Every lane adds in the order the
+// team's lane 0 does (lower lane's point first), so all lanes end with the same representation of the sum.
+PLUME_DEV jac jac_team_sum(uint32_t mask, jac p, uint32_t q, int levels) {
+    for (int l = 0; l < levels; l++) {
+        jac o = jac_shfl_xor(mask, p, 1 << l);
+        p = ((q >> l) & 1) ? jac_add(o, p) : jac_add(p, o);
+    }
+    return p;
+}
+#endif
+
 // affine from Jacobian given zinv = 1/Z (canonical coordinates)
 PLUME_DEV aff aff_from_jac_zinv(const jac& p, const fe& zinv) {
     aff r;

@@ -261,3 +261,15 @@ PLUME_DEV jac h2c_hash_to_curve(const uint8_t* msg, uint32_t len, const uint8_t*
     }
     return jac_add(q[0], q[1]);
 }
+
+#ifndef PLUME_HOSTSIM
+// Small batches: the two field elements of one item are mapped on two neighbouring lanes (j = 0, 1), which halves the serial
+// work (two exponentiations of 254 squarings dominate hash_to_curve).  Both lanes hash (cheap) and both return Q0 + Q1.
+PLUME_DEV jac h2c_hash_to_curve_team(uint32_t mask, uint32_t j, const uint8_t* msg, uint32_t len, const uint8_t* extra, uint32_t nextra) {
+    fe u0, u1;
+    h2c_hash_to_field(u0, u1, msg, len, extra, nextra);
+    fe xn, xd, y;
+    h2c_map_sswu(xn, xd, y, j == 0 ? u0 : u1);
+    return jac_team_sum(mask, h2c_iso_map(xn, xd, y), j, 1);
+}
+#endif

@@ -35,7 +35,11 @@ __global__ void __launch_bounds__(128) k_h2c_out(h2c_args a) {
 }
 __global__ void __launch_bounds__(128) k_binv(uint32_t* Z, uint32_t* scratch, uint32_t m, uint32_t T) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < T) binv_body(t, T, Z, scratch, m);
+    if (t < T) binv_body<false>(t, T, Z, scratch, m);
+}
+__global__ void __launch_bounds__(128) k_binv_var(uint32_t* Z, uint32_t* scratch, uint32_t m, uint32_t T) {   // small batches
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T) binv_body<true>(t, T, Z, scratch, m);
 }
 __global__ void k_gtab_bases(uint32_t* bases, int w) {
     if (blockIdx.x == 0 && threadIdx.x == 0) gtab_bases_body(bases, w);
@@ -72,6 +76,7 @@ __global__ void __launch_bounds__(128) k_debug_fe_op(int op, uint32_t n, const u
         case 2: r = fe_add(x, y); break;
         case 3: r = fe_sub(x, y); break;
         case 4: r = fe_inv(x); break;
+        case 14: r = fe_inv_var(x); break;
         case 5: r = fe_norm(x); break;
         case 6: r = fe_mul_small(x, y.v[0]); break;
         case 7: r = fe_pow_pm3d4(x); break;
@@ -171,11 +176,12 @@ cudaError_t launch_h2c_out(const h2c_args& a, cudaStream_t s) {
     k_h2c_out<<<grid_for(a.n, 128), 128, 0, s>>>(a);
     return cudaGetLastError();
 }
-cudaError_t launch_binv(uint32_t* Z, uint32_t* scratch, uint32_t m, uint32_t per_thread, cudaStream_t s) {
+cudaError_t launch_binv(uint32_t* Z, uint32_t* scratch, uint32_t m, uint32_t per_thread, cudaStream_t s, bool var) {
     if (per_thread < 1) per_thread = 1;
     uint32_t T = (m + per_thread - 1) / per_thread;
     T = (T + 31) / 32 * 32;  // whole warps so that the strided accesses stay coalesced
-    k_binv<<<grid_for(T, 128), 128, 0, s>>>(Z, scratch, m, T);
+    if (var) k_binv_var<<<grid_for(T, 128), 128, 0, s>>>(Z, scratch, m, T);
+    else k_binv<<<grid_for(T, 128), 128, 0, s>>>(Z, scratch, m, T);
     return cudaGetLastError();
 }
 cudaError_t launch_gtab_bases(uint32_t* bases, int w, cudaStream_t s) {

@@ -39,13 +39,21 @@ cudaError_t launch_verify_tab_b(const verify_args& a, cudaStream_t s);   // the 
 cudaError_t launch_verify_lad_b(const verify_args& a, cudaStream_t s);   // ... and its double-base ladder
 cudaError_t launch_verify_mul_a(const verify_args& a, cudaStream_t s);   // G*s - pk*c
 cudaError_t launch_verify_final(const verify_args& a, cudaStream_t s);
+// small batches (k_team.cu): 2 or 4 neighbouring lanes per item, same workspace conventions as the kernels above
+cudaError_t launch_sign_fixed_team(const sign_args& a, cudaStream_t s);
+cudaError_t launch_sign_h2c_team(const sign_args& a, cudaStream_t s);
+cudaError_t launch_sign_comb_lad_team(const sign_args& a, cudaStream_t s);
+cudaError_t launch_verify_h2c_team(const verify_args& a, cudaStream_t s);
+cudaError_t launch_verify_lad_b_team(const verify_args& a, cudaStream_t s);
+cudaError_t launch_verify_mul_a_team(const verify_args& a, cudaStream_t s);
 cudaError_t launch_h2c_map(const h2c_args& a, cudaStream_t s);
 cudaError_t launch_h2c_out(const h2c_args& a, cudaStream_t s);
 cudaError_t launch_h2cw(int stage, const h2cw_args& a, cudaStream_t s);   // 0 map, 1 sum, 2 out
 cudaError_t launch_fbmul(int stage, const fbmul_args& a, cudaStream_t s);   // 0 map, 1 out
 cudaError_t launch_registers(uint32_t n, const uint8_t* in32, uint64_t* out4, cudaStream_t s);
-// batched inversion of m elements at Z (scratch same size), `per_thread` elements per thread
-cudaError_t launch_binv(uint32_t* Z, uint32_t* scratch, uint32_t m, uint32_t per_thread, cudaStream_t s);
+// batched inversion of m elements at Z (scratch same size), `per_thread` elements per thread; `var`: the division-step
+// inversion (inv.cuh; small batches, where the one inversion per thread is what the caller waits for)
+cudaError_t launch_binv(uint32_t* Z, uint32_t* scratch, uint32_t m, uint32_t per_thread, cudaStream_t s, bool var = false);
 // generator table
 cudaError_t launch_gtab_bases(uint32_t* bases, int w, cudaStream_t s);
 cudaError_t launch_gtab_entries(uint32_t ne, uint32_t* tab, uint32_t* zs, const uint32_t* bases, int w, cudaStream_t s);

@@ -178,6 +178,45 @@ PLUME_DEV jac vb_mul_tab(const sc& k, const uint32_t* tab, const fe& zg) {
     return acc;
 }
 
+// Windows [j0, j1) of fb_mul (the small-batch kernels split one scalar over two lanes); j0 = 0, j1 = fb_windows(w): all.
+PLUME_DEV int fb_windows(int w) { return (256 + w - 1) / w; }
+PLUME_DEV jac fb_mul_windows(const sc& k, const uint32_t* gtab, int w, int j0, int j1) {
+    uint32_t s[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i] = k.v[i];
+    const uint32_t mask = (1u << w) - 1;
+    jac acc = jac_infinity();
+#pragma unroll 1
+    for (int j = 0; j < j1; j++) {
+        uint32_t d = s[0] & mask;
+#pragma unroll
+        for (int i = 0; i < 7; i++) s[i] = (s[i] >> w) | (s[i + 1] << (32 - w));
+        s[7] >>= w;
+        if (d != 0 && j >= j0) {
+            const uint32_t* e = gtab + (((size_t)j << w) + d) * 16;
+            acc = jac_add_aff(acc, ent_ld_fe(e), ent_ld_fe(e + 8), 0);
+        }
+    }
+    return acc;
+}
+
+// The share of ONE half-scalar in the ladders above and below, for the small-batch kernels: the half-scalars of an item run
+// on neighbouring lanes, each with all the doublings and a quarter (Straus) or half of the additions, and the lanes' points
+// are added at the end.  The result lives on the table's isomorphic curve: the caller multiplies Z by Zg after the sum.
+PLUME_DEV jac vb_ladder_half(const glv_half& h, bool endo, const uint32_t* tab) {
+    booth_reg b = booth_init(h);
+    jac acc = jac_infinity();
+#pragma unroll 1
+    for (int i = 32; i >= 0; i--) {
+        if (i < 32) {
+#pragma unroll 1
+            for (int j = 0; j < 4; j++) acc = jac_dbl_fast(acc);
+        }
+        acc = vb_add_digit(acc, booth_next(b), h.neg, endo, tab);
+    }
+    return acc;
+}
+
 // k1 * P1 + k2 * P2 with shared doublings (Straus): both tables must be expressed on the same
 // isomorphic curve (common denominator zg), see vb_build_table_pair.
 PLUME_DEV jac vb_mul2_tab(const sc& k1, const uint32_t* tab1, const sc& k2, const uint32_t* tab2, const fe& zg) {
@@ -422,6 +461,24 @@ PLUME_DEV jac comb_mul_tab(const sc& k, const uint32_t* tab, const fe& zg, const
         }
     }
     if (!acc.inf) acc.z = fe_mul(acc.z, zg);
+    return acc;
+}
+
+// One half-scalar's share of comb_mul_tab (small-batch kernels; see vb_ladder_half), parity correction included, on the
+// table's isomorphic curve.
+PLUME_DEV jac comb_ladder_half(const glv_half& h, bool endo, const uint32_t* tab, const fe& pxs, const fe& pys) {
+    comb_rows r = comb_recode(h);
+    jac acc = jac_infinity();
+#pragma unroll 1
+    for (int c = COMB_D - 1; c >= 0; c--) {
+        if (c < COMB_D - 1) acc = jac_dbl_fast(acc);
+        acc = comb_add_column(acc, r, c, endo, tab);
+    }
+    if (r.even) {
+        fe x = endo ? fe_mul(pxs, ec_beta()) : pxs;
+        fe y = r.neg ? pys : fe_neg(pys);
+        acc = jac_add_aff(acc, x, y, 0);
+    }
     return acc;
 }
 

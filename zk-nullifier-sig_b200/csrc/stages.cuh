@@ -23,6 +23,7 @@
 //   V3 affine A, B; (V1: compare with r_point, hashed_to_curve_r); c == SHA-256(...) mod n  [verify_stage_final]
 #pragma once
 #include "h2c.cuh"
+#include "inv.cuh"
 #include "mul.cuh"
 
 // ---- status codes (include/plume_b200.h) ---------------------------------------------------------
@@ -491,7 +492,9 @@ PLUME_DEV void sign_stage_final(uint32_t i, const sign_args& a) {
 // ---- batched inversion ---------------------------------------------------------------------------------
 // Z[0..m) in place -> 1/Z (0 stays 0).  Thread t of T owns elements t, t+T, t+2T, ... (coalesced),
 // multiplies them into a running product, inverts once, and walks back (Montgomery's trick):
-// 3 multiplications per element + one ~270-multiplication inversion per K elements.
+// 3 multiplications per element + one ~270-multiplication inversion per K elements.  VAR: the inversion by division steps
+// (inv.cuh) instead of Fermat's -- a quarter of the latency, which is what a small batch waits for.
+template <bool VAR = false>
 PLUME_DEV void binv_body(uint32_t t, uint32_t T, uint32_t* Z, uint32_t* scratch, uint32_t m) {
     fe acc = fe_one();
     uint32_t cnt = 0;
@@ -502,7 +505,7 @@ PLUME_DEV void binv_body(uint32_t t, uint32_t T, uint32_t* Z, uint32_t* scratch,
         if (!fe_is_zero(z)) acc = fe_mul(acc, z);
     }
     if (cnt == 0) return;
-    fe inv = fe_inv(acc);
+    fe inv = VAR ? fe_inv_var(acc) : fe_inv(acc);
 #pragma unroll 1
     for (uint32_t j = cnt; j-- > 0;) {
         uint32_t idx = t + j * T;
@@ -534,9 +537,10 @@ struct verify_args {
 };
 
 // ok[i] is used as scratch between stages: 1 = inputs well-formed so far, 0 = reject
-PLUME_DEV void verify_stage_h2c(uint32_t i, const verify_args& a) {
+// the input checks of verify_stage_h2c; pk33 / the return value: the SEC1 form of pk (of G for a rejected item)
+PLUME_DEV uint32_t verify_h2c_check(uint32_t i, const verify_args& a, uint8_t* pk33, bool& good) {
     aff pk, nul;
-    bool good = ld_point_be(pk, a.pk + (size_t)i * 64);
+    good = ld_point_be(pk, a.pk + (size_t)i * 64);
     good = ld_point_be(nul, a.nullifier + (size_t)i * 64) && good;
     sc c = ld_sc_be(a.c + (size_t)i * 32), s = ld_sc_be(a.s + (size_t)i * 32);
     const bool ark = a.flavour == PLUME_FLAVOUR_ARKWORKS;
@@ -547,10 +551,14 @@ PLUME_DEV void verify_stage_h2c(uint32_t i, const verify_args& a) {
         good = ld_point_be(t, a.r_point + (size_t)i * 64) && good;
         good = ld_point_be(t, a.hashed_to_curve_r + (size_t)i * 64) && good;
     }
-    a.ok[i] = good ? 1 : 0;
     if (!good) pk = aff_generator();  // keep the lane on the common path; result is discarded
+    return enc_point33(pk33, pk);
+}
+PLUME_DEV void verify_stage_h2c(uint32_t i, const verify_args& a) {
     uint8_t pk33[33];
-    uint32_t npk = enc_point33(pk33, pk);
+    bool good;
+    uint32_t npk = verify_h2c_check(i, a, pk33, good);
+    a.ok[i] = good ? 1 : 0;
     uint32_t len;
     const uint8_t* m = msg_ptr(a.msgs, i, len);
     jac h = h2c_hash_to_curve(m, len, pk33, npk);  // lib.rs:103

@@ -1,0 +1,153 @@
+// stages_team.cuh -- the stages of stages.cuh for SMALL batches: a team of 2 or 4 neighbouring lanes per item.
+//
+// The throughput kernels give one thread one item (or one scalar), which is what fills the machine at 10^5 items and more.
+// A batch of one -- the call shape of the reference's sign_v1 / sign_v2 / verify (rust-k256/src/lib.rs:149-156, :99) -- then
+// runs ~3 700 field operations one after the other on one lane of one warp.  These bodies shorten that chain by giving the
+// independent parts of a stage to neighbouring lanes and adding the lanes' points with shuffles at the end:
+//
+//   hash_to_curve          2 lanes: the two SSWU maps (one 254-squaring exponentiation each)
+//   g^r, g^sk              2 lanes: one scalar each
+//   h^r, h^sk (comb)       4 lanes: (scalar, GLV half); all the doublings and half the additions each
+//   h*s - nul*c (Straus)   4 lanes: one of the four half-scalars each (all doublings, a quarter of the additions)
+//   G*s - pk*c             4 lanes: the two GLV halves of -c*pk, and the two halves of the generator windows of s
+//
+// Results are the same points in another Jacobian representation, so the outputs (affine, canonical) are bit-identical to
+// the throughput path's; tests/test_gpu_parity.py runs both on the same inputs against the oracle.  Device code only.
+#pragma once
+#include "stages.cuh"
+
+// `mask`: the warp's lanes whose team is inside the batch (teams are whole: the kernels are launched on T * n threads).
+
+PLUME_DEV void sign_stage_fixed_team(uint32_t idx, const sign_args& a) {   // 2 lanes, no exchange
+    const uint32_t i = idx >> 1, j = idx & 1;
+    sc r = ld_sc_be(a.r + (size_t)i * 32);
+    sc sk = ld_sc_be(a.sk + (size_t)i * 32);
+    uint8_t st = PLUME_ST_OK;
+    if (a.flavour == PLUME_FLAVOUR_ARKWORKS) {
+        if (sc_ge_n(sk)) { st = PLUME_ST_BAD_SK; sk = sc_one(); }
+        if (sc_ge_n(r)) { st = PLUME_ST_BAD_R; r = sc_one(); }
+        aff P;
+        if (!ld_point_be(P, a.pk_in + (size_t)i * 64) || P.inf) { st = PLUME_ST_BAD_PK; P = aff_generator(); }
+        if (j == 0) {
+            a.status[i] = st;
+            ws_store_jac(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i, fb_mul(r, a.gtab, a.gw));
+        } else {
+            ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, jac_from_aff(P));
+        }
+        return;
+    }
+    if (!sc_is_valid_nonzero(sk)) { st = PLUME_ST_BAD_SK; sk = sc_one(); }
+    if (!sc_is_valid_nonzero(r)) { st = PLUME_ST_BAD_R; r = sc_one(); }
+    if (j == 0) a.status[i] = st;
+    jac P = fb_mul(j == 0 ? r : sk, a.gtab, a.gw);
+    st_fe(ws_at(a.ws, a.n, j == 0 ? WS_AX : WS_BX, i), P.x);
+    st_fe(ws_at(a.ws, a.n, j == 0 ? WS_AY : WS_BY, i), P.y);
+    st_fe(ws_at(a.ws, a.n, j == 0 ? WS_Z0 : WS_Z1, i), P.z);
+}
+
+PLUME_DEV void sign_stage_h2c_team(uint32_t mask, uint32_t idx, const sign_args& a) {   // 2 lanes
+    const uint32_t i = idx >> 1, j = idx & 1;
+    aff R = ws_load_affine(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i);
+    aff K = ws_load_affine(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i);
+    if (j == 0) {
+        ws_store_aff(a.ws, a.n, WS_RX, WS_RY, i, R);
+        ws_store_aff(a.ws, a.n, WS_KX, WS_KY, i, K);
+    }
+    uint8_t pk33[33];
+    uint32_t npk = enc_point33(pk33, K);
+    uint32_t len;
+    const uint8_t* m = msg_ptr(a.msgs, i, len);
+    jac h = h2c_hash_to_curve_team(mask, j, m, len, pk33, npk);   // (both lanes have read WS_Z0 before the exchange inside)
+    if (j == 0) ws_store_jac(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i, h);
+}
+
+// h^r, h^sk from the comb table of sign_stage_varbase_tab: lane q = 2 * (0: r, 1: sk) + (GLV half)
+PLUME_DEV void sign_stage_varbase_lad_team(uint32_t mask, uint32_t idx, const sign_args& a, const uint32_t* vbtab) {
+    const uint32_t i = idx >> 2, q = idx & 3, which = q >> 1;
+    fe zg = ld_fe(ws_at(a.ws, a.n, WS_P0, i));
+    mask = __ballot_sync(mask, !fe_is_zero(zg));
+    if (fe_is_zero(zg)) return;   // h was the identity: the table stage stored the results (the whole team leaves)
+    fe hx = ld_fe(ws_at(a.ws, a.n, WS_HX, i)), hy = ld_fe(ws_at(a.ws, a.n, WS_HY, i));
+    fe zg2 = fe_sqr(zg);
+    fe hxs = fe_mul(hx, zg2), hys = fe_mul(hy, fe_mul(zg2, zg));
+    sc k = ld_sc_be((which ? a.sk : a.r) + (size_t)i * 32);
+    const bool zero_ok = a.flavour == PLUME_FLAVOUR_ARKWORKS;
+    if (sc_ge_n(k) || (!zero_ok && sc_is_zero(k))) k = sc_one();
+    glv_half h1, h2;
+    glv_split(k, h1, h2);
+    jac o = comb_ladder_half((q & 1) ? h2 : h1, (q & 1) != 0, vbtab + (size_t)i * VB_ITEM_WORDS, hxs, hys);
+    o = jac_team_sum(mask, o, q & 1, 1);
+    if (q & 1) return;
+    if (!o.inf) o.z = fe_mul(o.z, zg);
+    if (which == 0) ws_store_jac(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i, o);
+    else ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, o);
+}
+
+PLUME_DEV void verify_stage_h2c_team(uint32_t mask, uint32_t idx, const verify_args& a) {   // 2 lanes
+    const uint32_t i = idx >> 1, j = idx & 1;
+    uint8_t pk33[33];
+    bool good;
+    uint32_t npk = verify_h2c_check(i, a, pk33, good);
+    if (j == 0) a.ok[i] = good ? 1 : 0;
+    uint32_t len;
+    const uint8_t* m = msg_ptr(a.msgs, i, len);
+    jac h = h2c_hash_to_curve_team(mask, j, m, len, pk33, npk);
+    if (j == 0) ws_store_jac(a.ws, a.n, WS_HX, WS_HY, WS_Z1, i, h);
+}
+
+// B = s*h - c*nul from the tables of verify_stage_mul_b1: lane q = 2 * (0: s on h, 1: -c on nul) + (GLV half)
+PLUME_DEV void verify_stage_mul_b2_team(uint32_t mask, uint32_t idx, const verify_args& a, const uint32_t* vbtab) {
+    const uint32_t i = idx >> 2, q = idx & 3;
+    const bool todo = ld_fe(ws_at(a.ws, a.n, WS_RY, i)).v[0] != 0;
+    mask = __ballot_sync(mask, todo);
+    if (!todo) return;   // finished in b1 (the whole team leaves)
+    sc k = sc_one();
+    if (a.ok[i] != 0) {
+        k = ld_sc_be((q < 2 ? a.s : a.c) + (size_t)i * 32);
+        if (q >= 2) k = sc_neg(k);
+    }
+    glv_half h1, h2;
+    glv_split(k, h1, h2);
+    const uint32_t* tab = vbtab + (size_t)i * VB_ITEM_WORDS + (q < 2 ? 0 : VB_TAB_WORDS);
+    jac B = vb_ladder_half((q & 1) ? h2 : h1, (q & 1) != 0, tab);
+    B = jac_team_sum(mask, B, q, 2);
+    if (q != 0) return;
+    if (!B.inf) B.z = fe_mul(B.z, ld_fe(ws_at(a.ws, a.n, WS_KX, i)));
+    ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, B);
+}
+
+// A = s*G - c*pk: lanes 0, 1 the GLV halves of -c on pk's window table (lane 0 builds it), lanes 2, 3 the lower and upper
+// generator windows of s
+PLUME_DEV void verify_stage_mul_a_team(uint32_t mask, uint32_t idx, const verify_args& a, uint32_t* tab) {
+    const uint32_t i = idx >> 2, q = idx & 3;
+    aff pk;
+    sc c = sc_one(), s = sc_one();
+    if (a.ok[i] != 0) {
+        ld_point_be(pk, a.pk + (size_t)i * 64);
+        c = ld_sc_be(a.c + (size_t)i * 32);
+        s = ld_sc_be(a.s + (size_t)i * 32);
+    } else {
+        pk = aff_generator();
+    }
+    fe zg = fe_one();
+    if (q == 0 && !pk.inf) zg = vb_build_table(pk.x, pk.y, tab, true);
+    __syncwarp(mask);    // the table is in global scratch: ordered for the team's lane 1 by the barrier
+    jac A;
+    if (q < 2) {
+        A = jac_infinity();
+        if (!pk.inf) {
+            glv_half h1, h2;
+            glv_split(sc_neg(c), h1, h2);
+            A = vb_ladder_half(q ? h2 : h1, q != 0, tab);
+        }
+    } else {
+        const int nw = fb_windows(a.gw), mid = nw / 2;
+        A = fb_mul_windows(s, a.gtab, a.gw, q == 2 ? 0 : mid, q == 2 ? mid : nw);
+    }
+    A = jac_team_sum(mask, A, q & 1, 1);
+    if (q == 0 && !A.inf) A.z = fe_mul(A.z, zg);   // back from the table's isomorphic curve (only lane 0's sum is used)
+    jac o = jac_shfl_xor(mask, A, 2);
+    if (q != 0) return;
+    A = jac_add(o, A);    // fixed-base part first, as verify_stage_mul_a does
+    ws_store_jac(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i, A);
+}
