@@ -38,6 +38,18 @@ fixed = rng.integers(0, 256, (n, 32), dtype=np.uint8)
 o = ctx.sign_batch(1, fixed, sk, r)
 ctx.verify_batch(1, fixed, o["pk"], o["nullifier"], o["c"], o["s"], o["r_point"], o["hashed_to_curve_r"])
 ctx.hash_to_curve_batch(rng.integers(0, 256, (n, 65), dtype=np.uint8))
+# the small-batch (team) kernels with part of a warp and part of a team's block unused, and the library's self test
+for k in (1, 3, 33):
+    o = ctx.sign_batch(1, fixed[:k], sk[:k], r[:k])
+    ctx.verify_batch(1, fixed[:k], o["pk"], o["nullifier"], o["c"], o["s"], o["r_point"], o["hashed_to_curve_r"])
+ctx.self_test()
+# the throughput kernels on the same small batch (PLUME_TEAM_MAX=0), as a 2^20 batch runs them
+os.environ["PLUME_TEAM_MAX"] = "0"
+t = P.PlumeContext(0, 8)
+del os.environ["PLUME_TEAM_MAX"]
+o = t.sign_batch(1, msgs, sk, r)
+t.verify_batch(1, msgs, o["pk"], o["nullifier"], o["c"], o["s"], o["r_point"], o["hashed_to_curve_r"])
+t.close()
 big = 9000
 bm = rng.integers(0, 256, (big, 32), dtype=np.uint8)
 bs = rng.integers(0, 256, (big, 32), dtype=np.uint8); bs[:, 0] &= 0x7F
