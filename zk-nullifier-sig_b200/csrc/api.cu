@@ -94,7 +94,7 @@ int run_stage(plume_ctx* ctx, int stage, cudaStream_t s, F&& launch) {
 int binv(plume_ctx* ctx, uint32_t* ws, uint32_t n, uint32_t m, cudaStream_t s, int slot = WS_Z0) {
     // small batches: short chains (4 elements per inversion) and the division-step inversion -- latency, not throughput
     const bool small = n <= ctx->team_max;
-    RUN(ST_BINV, launch_binv(ws + (size_t)slot * n * 8, ws + (size_t)WS_P0 * n * 8, m, small ? 4u : ctx->binv_k, s, small));
+    RUN(ST_BINV, launch_binv(ws + (size_t)slot * n * 8, ws + (size_t)WS_P0 * n * 8, m, small ? 4u : ctx->binv_k, s, small || ctx->binv_var));
     return PLUME_OK;
 }
 
@@ -507,6 +507,7 @@ int ctx_create_single(plume_ctx** out, int device, int fixed_window_bits, const 
     if (c->host_chunk > c->chunk) c->host_chunk = c->chunk;
     c->binv_k = (uint32_t)env_size("PLUME_BINV_K", 32);   // elements per inversion: 8 -> 0.42 ms per 2^21 elements, 16 -> 0.27, 32 -> 0.21, 64 -> 0.21
     c->stage_threads = (int)env_size("PLUME_STAGE_THREADS", 8);
+    c->binv_var = env_size("PLUME_BINV_VAR", 0) != 0;
     if (const char* e = getenv("PLUME_TEAM_MAX")) c->team_max = (uint32_t)strtoul(e, nullptr, 10);   // 0 switches the small-batch kernels off
     { const char* v = getenv("PLUME_DEVICE_SPLIT"); c->dev_split = !(v && v[0] == '0'); }
     struct Guard { plume_ctx* c; ~Guard() { if (c) plume_ctx_destroy(c); } } guard{c};

@@ -44,6 +44,7 @@ struct plume_ctx {
     size_t chunk = 0;        // largest n of one pass (what the `_device` entry points accept)
     size_t host_chunk = 0;   // pipelining granularity of the host-pointer entry points
     uint32_t binv_k = 32;
+    bool binv_var = false;      // division-step inversion in the batched inversion of LARGE batches too (PLUME_BINV_VAR=1; measurement)
     uint32_t team_max = 4096;   // batches of at most this many items run the small-batch kernels (k_team.cu); 0: never
     int stage_threads = 8;   // threads of a staging memcpy (pageable callers)
     CopyPool* copy_pool = nullptr;   // created when the first pageable pointer shows up
