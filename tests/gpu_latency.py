@@ -17,9 +17,11 @@ def make(team_max, window=16):
 
 
 rng = np.random.default_rng(3)
-for label, team_max in (("team kernels", 32768), ("throughput kernels", 0)):
+CONFIGS = (("team kernels", 4096),) if os.environ.get("LAT_ONLY_TEAM") else (("team kernels", 32768), ("throughput kernels", 0))
+SIZES = (1, 1024, 4096) if os.environ.get("LAT_ONLY_TEAM") else (1, 32, 1024, 4096, 8192, 16384, 32768)
+for label, team_max in CONFIGS:
     ctx = make(team_max)
-    for n in (1, 32, 1024, 4096, 8192, 16384, 32768):
+    for n in SIZES:
         msgs = rng.integers(0, 256, (n, 32), dtype=np.uint8)
         sk = rng.integers(0, 256, (n, 32), dtype=np.uint8); sk[:, 0] &= 0x7F
         r = rng.integers(0, 256, (n, 32), dtype=np.uint8); r[:, 0] &= 0x7F

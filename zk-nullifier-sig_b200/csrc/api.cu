@@ -110,7 +110,7 @@ int enqueue_sign(plume_ctx* ctx, sign_args a, cudaStream_t s) {
 #ifdef PLUME_SIGN_ONE_KERNEL
     RUN(ST_SIGN_VARBASE, launch_sign_varbase(a, s));
 #else
-    RUN(ST_SIGN_TAB, launch_sign_comb_tab(a, s));
+    RUN(ST_SIGN_TAB, team ? launch_sign_comb_tab_small(a, s) : launch_sign_comb_tab(a, s));
     RUN(ST_SIGN_VARBASE, team ? launch_sign_comb_lad_team(a, s) : launch_sign_comb_lad(a, s));
 #endif
     if (int rc = binv(ctx, a.ws, a.n, 2 * a.n, s)) return rc;
@@ -135,7 +135,7 @@ int enqueue_verify(plume_ctx* ctx, verify_args a, cudaStream_t s) {
     if (int rc = binv(ctx, a.ws, a.n, a.n, s, WS_Z1)) return rc;
     // separate kernels, each with its own register budget: one fused kernel needs 168 registers (12 warps/SM), the
     // ladders alone run at 128 or fewer (16-24 warps/SM); 18 % faster in total (round 1)
-    RUN(ST_VERIFY_TAB_B, launch_verify_tab_b(a, s));
+    RUN(ST_VERIFY_TAB_B, team ? launch_verify_tab_b_small(a, s) : launch_verify_tab_b(a, s));
     RUN(ST_VERIFY_MUL_B, team ? launch_verify_lad_b_team(a, s) : launch_verify_lad_b(a, s));
     if (fork) CU(cudaStreamWaitEvent(s, ctx->ev_join, 0));
     else RUN(ST_VERIFY_MUL_A, team ? launch_verify_mul_a_team(a, s) : launch_verify_mul_a(a, s));

@@ -39,7 +39,10 @@ cudaError_t launch_verify_tab_b(const verify_args& a, cudaStream_t s);   // the 
 cudaError_t launch_verify_lad_b(const verify_args& a, cudaStream_t s);   // ... and its double-base ladder
 cudaError_t launch_verify_mul_a(const verify_args& a, cudaStream_t s);   // G*s - pk*c
 cudaError_t launch_verify_final(const verify_args& a, cudaStream_t s);
-// small batches (k_team.cu): 2 or 4 neighbouring lanes per item, same workspace conventions as the kernels above
+// small batches (k_team.cu, k_team_lad.cu): 2 or 4 neighbouring lanes per item, same workspace conventions as the kernels
+// above; `_small`: one lane per item, the table builders compiled for latency
+cudaError_t launch_sign_comb_tab_small(const sign_args& a, cudaStream_t s);
+cudaError_t launch_verify_tab_b_small(const verify_args& a, cudaStream_t s);
 cudaError_t launch_sign_fixed_team(const sign_args& a, cudaStream_t s);
 cudaError_t launch_sign_h2c_team(const sign_args& a, cudaStream_t s);
 cudaError_t launch_sign_comb_lad_team(const sign_args& a, cudaStream_t s);

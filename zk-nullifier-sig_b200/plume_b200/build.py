@@ -16,7 +16,7 @@ if PKG not in sys.path:
 CSRC = os.path.join(PKG, "csrc")
 BUILD = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libplume_b200.so")
-UNITS = ["api", "api_multi", "selftest", "k_sign", "k_verify", "k_misc", "k_team"]
+UNITS = ["api", "api_multi", "selftest", "k_sign", "k_verify", "k_misc", "k_team", "k_team_lad"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-no-compress"]
 
