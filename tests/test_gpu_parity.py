@@ -135,8 +135,9 @@ def test_hash_to_curve_batch(gpu_ctx):
     rnd = random.Random(25)
     msgs = [bytes(rnd.randrange(256) for _ in range(L)) for L in [0, 1, 3, 29, 32, 62, 63, 64, 65, 66, 127, 128, 129, 500] * 20]
     assert np.array_equal(gpu_ctx.hash_to_curve_batch(msgs), c_oracle.h2c_batch(msgs, threads=os.cpu_count() or 1))
-    fixed = np.random.default_rng(25).integers(0, 256, (4096, 65), dtype=np.uint8)
-    assert np.array_equal(gpu_ctx.hash_to_curve_batch(fixed), c_oracle.h2c_batch(fixed, threads=os.cpu_count() or 1))
+    fixed = np.random.default_rng(25).integers(0, 256, (6000, 65), dtype=np.uint8)
+    for n in (1, 3, 33, 4096, 4097, 6000):     # two lanes per item up to 4 096 items, one thread per item above
+        assert np.array_equal(gpu_ctx.hash_to_curve_batch(fixed[:n]), c_oracle.h2c_batch(fixed[:n], threads=os.cpu_count() or 1)), n
 
 
 def test_chunk_boundaries_of_host_api():
@@ -369,6 +370,7 @@ def test_small_batches_on_the_throughput_kernels(throughput_ctx):
     test_fixed_length_records(throughput_ctx)
     test_tampered_and_malformed_verify_inputs(throughput_ctx)
     test_identity_forgery_agrees_with_oracle(throughput_ctx)
+    test_hash_to_curve_batch(throughput_ctx)
     import test_arkworks_flavour as A
     A.test_gpu_ark_sign_and_verify_match_oracle(throughput_ctx)
     throughput_ctx.self_test()

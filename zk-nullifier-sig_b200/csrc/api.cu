@@ -144,7 +144,7 @@ int enqueue_verify(plume_ctx* ctx, verify_args a, cudaStream_t s) {
     return PLUME_OK;
 }
 int enqueue_h2c(plume_ctx* ctx, h2c_args a, cudaStream_t s) {
-    RUN(ST_H2C_MAP, launch_h2c_map(a, s));
+    RUN(ST_H2C_MAP, a.n <= ctx->team_max ? launch_h2c_map_team(a, s) : launch_h2c_map(a, s));
     if (int rc = binv(ctx, a.ws, a.n, a.n, s)) return rc;
     RUN(ST_H2C_OUT, launch_h2c_out(a, s));
     return PLUME_OK;

@@ -43,6 +43,7 @@ cudaError_t launch_verify_final(const verify_args& a, cudaStream_t s);
 // above; `_small`: one lane per item, the table builders compiled for latency
 cudaError_t launch_sign_comb_tab_small(const sign_args& a, cudaStream_t s);
 cudaError_t launch_verify_tab_b_small(const verify_args& a, cudaStream_t s);
+cudaError_t launch_h2c_map_team(const h2c_args& a, cudaStream_t s);
 cudaError_t launch_sign_fixed_team(const sign_args& a, cudaStream_t s);
 cudaError_t launch_sign_h2c_team(const sign_args& a, cudaStream_t s);
 cudaError_t launch_sign_comb_lad_team(const sign_args& a, cudaStream_t s);

@@ -5,7 +5,7 @@
 // runs ~3 700 field operations one after the other on one lane of one warp.  These bodies shorten that chain by giving the
 // independent parts of a stage to neighbouring lanes and adding the lanes' points with shuffles at the end:
 //
-//   hash_to_curve          2 lanes: the two SSWU maps (one 254-squaring exponentiation each)
+//   hash_to_curve          2 lanes: the two SSWU maps (one 254-squaring exponentiation each); also plume_hash_to_curve_batch
 //   g^r, g^sk              2 lanes: one scalar each
 //   h^r, h^sk (comb)       4 lanes: (scalar, GLV half); all the doublings and half the additions each
 //   h*s - nul*c (Straus)   4 lanes: one of the four half-scalars each (all doublings, a quarter of the additions)
@@ -93,6 +93,23 @@ PLUME_DEV void verify_stage_h2c_team(uint32_t mask, uint32_t idx, const verify_a
     const uint8_t* m = msg_ptr(a.msgs, i, len);
     jac h = h2c_hash_to_curve_team(mask, j, m, len, pk33, npk);
     if (j == 0) ws_store_jac(a.ws, a.n, WS_HX, WS_HY, WS_Z1, i, h);
+}
+
+// hash_to_curve alone (h2c_stage_map), 2 lanes
+PLUME_DEV void h2c_stage_map_team(uint32_t mask, uint32_t idx, const h2c_args& a) {
+    const uint32_t i = idx >> 1, j = idx & 1;
+    uint32_t len;
+    const uint8_t* m = msg_ptr(a.msgs, i, len);
+    jac h;
+    if (a.pk33) {
+        uint8_t e[33];
+#pragma unroll 1
+        for (int k = 0; k < 33; k++) e[k] = a.pk33[(size_t)i * 33 + k];
+        h = h2c_hash_to_curve_team(mask, j, m, len, e, e[0] == 0 ? 1u : 33u);
+    } else {
+        h = h2c_hash_to_curve_team(mask, j, m, len, m, 0);
+    }
+    if (j == 0) ws_store_jac(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i, h);
 }
 
 // B = s*h - c*nul from the tables of verify_stage_mul_b1: lane q = 2 * (0: s on h, 1: -c on nul) + (GLV half)
