@@ -2,6 +2,14 @@
 // (see k_team.cu).  Besides the team ladders this holds one-lane-per-item copies of the two table builders: the same bodies as
 // k_sign_comb_tab / k_verify_tab_b, which a small batch runs between the team kernels.
 #define PLUME_INLINE_MUL
+// The signer's comb with 4 teeth here (5 in the throughput kernels): the chain a lone lane walks is 99 + 33 doublings, 7
+// conjugate additions for the 8 entries and 33 additions, against 104 + 26, 15 and 26 -- fewer operations in a row, more in
+// total.  Table and ladders of a small batch both come from this translation unit; the per-item scratch stride is the
+// (larger) one the library allocates for 5 teeth.
+#ifndef PLUME_TEAM_COMB_T
+#define PLUME_TEAM_COMB_T 4
+#endif
+#define PLUME_COMB_T PLUME_TEAM_COMB_T
 #include "team.h"
 
 __global__ void __launch_bounds__(128) k_sign_fixed_team(sign_args a) {
