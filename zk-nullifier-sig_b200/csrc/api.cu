@@ -91,10 +91,10 @@ int run_stage(plume_ctx* ctx, int stage, cudaStream_t s, F&& launch) {
     } while (0)
 
 // batched inversion of m workspace elements starting at slot `slot` (WS_Z0: both Z arrays when m = 2n; WS_Z1: the second)
-int binv(plume_ctx* ctx, uint32_t* ws, uint32_t n, uint32_t m, cudaStream_t s, int slot = WS_Z0) {
+int binv(plume_ctx* ctx, uint32_t* ws, uint32_t n, uint32_t m, cudaStream_t s, int slot = WS_Z0, int scratch_slot = WS_P0) {
     // small batches: short chains (4 elements per inversion) and the division-step inversion -- latency, not throughput
     const bool small = n <= ctx->team_max;
-    RUN(ST_BINV, launch_binv(ws + (size_t)slot * n * 8, ws + (size_t)WS_P0 * n * 8, m, small ? 4u : ctx->binv_k, s, small || ctx->binv_var));
+    RUN(ST_BINV, launch_binv(ws + (size_t)slot * n * 8, ws + (size_t)scratch_slot * n * 8, m, small ? 4u : ctx->binv_k, s, small || ctx->binv_var));
     return PLUME_OK;
 }
 
@@ -121,24 +121,44 @@ int enqueue_sign(plume_ctx* ctx, sign_args a, cudaStream_t s) {
 // dependent chain of stages, so independent stages are put on two streams (verify: G*s - pk*c next to h*s - nul*c).
 const uint32_t kSmallBatch = 8192;
 
+// The small-batch verifier (stages_team.cuh): G*s - pk*c on the second stream from the start (it needs only the inputs),
+// hash_to_curve, then tables and ladders of h*s - nul*c in one kernel on the Jacobian h, ONE batched inversion (Z of A, B, h).
+int enqueue_verify_team(plume_ctx* ctx, verify_args a, cudaStream_t s) {
+    const bool fork = ctx->aux_stream != nullptr;
+    if (fork) {
+        cudaStream_t sa = ctx->aux_stream;
+        CU(cudaEventRecord(ctx->ev_fork, s));
+        CU(cudaStreamWaitEvent(sa, ctx->ev_fork, 0));
+        if (int rc = run_stage(ctx, ST_VERIFY_MUL_A, sa, [&]() -> cudaError_t { return launch_verify_mul_a_team(a, sa); })) return rc;
+        CU(cudaEventRecord(ctx->ev_join, sa));
+    }
+    RUN(ST_VERIFY_H2C, launch_verify_h2c_team(a, s));
+    RUN(ST_VERIFY_MUL_B, launch_verify_mul_b_team(a, s));
+    if (fork) CU(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+    else RUN(ST_VERIFY_MUL_A, launch_verify_mul_a_team(a, s));
+    if (int rc = binv(ctx, a.ws, a.n, 3 * a.n, s, WS_RY, WS_Z0)) return rc;   // TV_ZA, TV_ZB, TV_ZH; scratch: the idle WS_Z0..WS_P0
+    RUN(ST_VERIFY_FINAL, launch_verify_final_team(a, s));
+    return PLUME_OK;
+}
+
 int enqueue_verify(plume_ctx* ctx, verify_args a, cudaStream_t s) {
+    if (a.n <= ctx->team_max) return enqueue_verify_team(ctx, a, s);
     const bool fork = a.n <= kSmallBatch && ctx->aux_stream != nullptr;
-    const bool team = a.n <= ctx->team_max;
-    RUN(ST_VERIFY_H2C, team ? launch_verify_h2c_team(a, s) : launch_verify_h2c(a, s));
+    RUN(ST_VERIFY_H2C, launch_verify_h2c(a, s));
     if (fork) {   // A needs the input checks of the first stage (ok[]) and nothing else: start it next to the stages of B
         cudaStream_t sa = ctx->aux_stream;
         CU(cudaEventRecord(ctx->ev_fork, s));
         CU(cudaStreamWaitEvent(sa, ctx->ev_fork, 0));
-        if (int rc = run_stage(ctx, ST_VERIFY_MUL_A, sa, [&]() -> cudaError_t { return team ? launch_verify_mul_a_team(a, sa) : launch_verify_mul_a(a, sa); })) return rc;
+        if (int rc = run_stage(ctx, ST_VERIFY_MUL_A, sa, [&]() -> cudaError_t { return launch_verify_mul_a(a, sa); })) return rc;
         CU(cudaEventRecord(ctx->ev_join, sa));
     }
     if (int rc = binv(ctx, a.ws, a.n, a.n, s, WS_Z1)) return rc;
     // separate kernels, each with its own register budget: one fused kernel needs 168 registers (12 warps/SM), the
     // ladders alone run at 128 or fewer (16-24 warps/SM); 18 % faster in total (round 1)
-    RUN(ST_VERIFY_TAB_B, team ? launch_verify_tab_b_small(a, s) : launch_verify_tab_b(a, s));
-    RUN(ST_VERIFY_MUL_B, team ? launch_verify_lad_b_team(a, s) : launch_verify_lad_b(a, s));
+    RUN(ST_VERIFY_TAB_B, launch_verify_tab_b(a, s));
+    RUN(ST_VERIFY_MUL_B, launch_verify_lad_b(a, s));
     if (fork) CU(cudaStreamWaitEvent(s, ctx->ev_join, 0));
-    else RUN(ST_VERIFY_MUL_A, team ? launch_verify_mul_a_team(a, s) : launch_verify_mul_a(a, s));
+    else RUN(ST_VERIFY_MUL_A, launch_verify_mul_a(a, s));
     if (int rc = binv(ctx, a.ws, a.n, 2 * a.n, s)) return rc;
     RUN(ST_VERIFY_FINAL, launch_verify_final(a, s));
     return PLUME_OK;

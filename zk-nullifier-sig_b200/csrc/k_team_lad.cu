@@ -1,6 +1,6 @@
 // k_team_lad.cu -- the small-batch kernels whose time is point arithmetic, compiled with the field multiplier inlined
-// (see k_team.cu).  Besides the team ladders this holds one-lane-per-item copies of the two table builders: the same bodies as
-// k_sign_comb_tab / k_verify_tab_b, which a small batch runs between the team kernels.
+// (see k_team.cu).  Besides the team ladders this holds a one-lane-per-item copy of the signer's table builder (the body of
+// k_sign_comb_tab), which a small batch runs between the team kernels.
 #define PLUME_INLINE_MUL
 // The signer's comb with 4 teeth here (5 in the throughput kernels): the chain a lone lane walks is 99 + 33 doublings, 7
 // conjugate additions for the 8 entries and 33 additions, against 104 + 26, 15 and 26 -- fewer operations in a row, more in
@@ -24,14 +24,9 @@ __global__ void __launch_bounds__(128) k_sign_comb_lad_team(sign_args a) {
     TEAM_PROLOGUE(4, a.n)
     sign_stage_varbase_lad_team(mask, idx, a, a.vbtab);
 }
-__global__ void __launch_bounds__(128) k_verify_tab_b_small(verify_args a) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < a.n)
-        verify_stage_mul_b1(i, a, a.vbtab + (size_t)i * VB_ITEM_WORDS, a.vbtab + (size_t)i * VB_ITEM_WORDS + VB_TAB_WORDS);
-}
-__global__ void __launch_bounds__(128) k_verify_lad_b_team(verify_args a) {
+__global__ void __launch_bounds__(128) k_verify_mul_b_team(verify_args a) {   // tables and ladders of h*s - nul*c
     TEAM_PROLOGUE(4, a.n)
-    verify_stage_mul_b2_team(mask, idx, a, a.vbtab);
+    verify_stage_mul_b_team(mask, idx, a, a.vbtab);
 }
 __global__ void __launch_bounds__(128) k_verify_mul_a_team(verify_args a) {
     TEAM_PROLOGUE(4, a.n)
@@ -40,6 +35,5 @@ __global__ void __launch_bounds__(128) k_verify_mul_a_team(verify_args a) {
 TEAM_LAUNCH(launch_sign_fixed_team, k_sign_fixed_team, sign_args, 2)
 TEAM_LAUNCH(launch_sign_comb_tab_small, k_sign_comb_tab_small, sign_args, 1)
 TEAM_LAUNCH(launch_sign_comb_lad_team, k_sign_comb_lad_team, sign_args, 4)
-TEAM_LAUNCH(launch_verify_tab_b_small, k_verify_tab_b_small, verify_args, 1)
-TEAM_LAUNCH(launch_verify_lad_b_team, k_verify_lad_b_team, verify_args, 4)
+TEAM_LAUNCH(launch_verify_mul_b_team, k_verify_mul_b_team, verify_args, 4)
 TEAM_LAUNCH(launch_verify_mul_a_team, k_verify_mul_a_team, verify_args, 4)

@@ -40,16 +40,16 @@ cudaError_t launch_verify_lad_b(const verify_args& a, cudaStream_t s);   // ... 
 cudaError_t launch_verify_mul_a(const verify_args& a, cudaStream_t s);   // G*s - pk*c
 cudaError_t launch_verify_final(const verify_args& a, cudaStream_t s);
 // small batches (k_team.cu, k_team_lad.cu): 2 or 4 neighbouring lanes per item, same workspace conventions as the kernels
-// above; `_small`: one lane per item, the table builders compiled for latency
+// above; `_small`: one lane per item, the signer's table builder compiled for latency
 cudaError_t launch_sign_comb_tab_small(const sign_args& a, cudaStream_t s);
-cudaError_t launch_verify_tab_b_small(const verify_args& a, cudaStream_t s);
 cudaError_t launch_h2c_map_team(const h2c_args& a, cudaStream_t s);
 cudaError_t launch_sign_fixed_team(const sign_args& a, cudaStream_t s);
 cudaError_t launch_sign_h2c_team(const sign_args& a, cudaStream_t s);
 cudaError_t launch_sign_comb_lad_team(const sign_args& a, cudaStream_t s);
 cudaError_t launch_verify_h2c_team(const verify_args& a, cudaStream_t s);
-cudaError_t launch_verify_lad_b_team(const verify_args& a, cudaStream_t s);
+cudaError_t launch_verify_mul_b_team(const verify_args& a, cudaStream_t s);    // tables and ladders of h*s - nul*c in one
 cudaError_t launch_verify_mul_a_team(const verify_args& a, cudaStream_t s);
+cudaError_t launch_verify_final_team(const verify_args& a, cudaStream_t s);
 cudaError_t launch_h2c_map(const h2c_args& a, cudaStream_t s);
 cudaError_t launch_h2c_out(const h2c_args& a, cudaStream_t s);
 cudaError_t launch_h2cw(int stage, const h2cw_args& a, cudaStream_t s);   // 0 map, 1 sum, 2 out

@@ -628,15 +628,8 @@ PLUME_DEV void verify_stage_mul_a(uint32_t i, const verify_args& a, uint32_t* ta
     ws_store_jac(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i, A);
 }
 
-PLUME_DEV void verify_stage_final(uint32_t i, const verify_args& a) {
-    bool good = a.ok[i] != 0;
-    if (!good) { a.ok[i] = 0; return; }
-    aff A = ws_load_affine(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i);
-    aff B = ws_load_affine(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i);
-    aff h;
-    h.x = ld_fe(ws_at(a.ws, a.n, WS_HX, i));
-    h.y = ld_fe(ws_at(a.ws, a.n, WS_HY, i));
-    h.inf = ld_fe(ws_at(a.ws, a.n, WS_RX, i)).v[0];
+// the checks of the last stage on the affine A = G*s - pk*c, B = h*s - nul*c and h
+PLUME_DEV void verify_final_check(uint32_t i, const verify_args& a, const aff& A, const aff& B, const aff& h) {
     aff pk, nul;
     ld_point_be(pk, a.pk + (size_t)i * 64);
     ld_point_be(nul, a.nullifier + (size_t)i * 64);
@@ -650,6 +643,17 @@ PLUME_DEV void verify_stage_final(uint32_t i, const verify_args& a) {
     sc d = sc_reduce256(plume_challenge(a.version, pk, h, nul, A, B));  // lib.rs:127-143
     sc c = ld_sc_be(a.c + (size_t)i * 32);
     a.ok[i] = sc_eq(c, d) ? 1 : 0;
+}
+PLUME_DEV void verify_stage_final(uint32_t i, const verify_args& a) {
+    bool good = a.ok[i] != 0;
+    if (!good) { a.ok[i] = 0; return; }
+    aff A = ws_load_affine(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i);
+    aff B = ws_load_affine(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i);
+    aff h;
+    h.x = ld_fe(ws_at(a.ws, a.n, WS_HX, i));
+    h.y = ld_fe(ws_at(a.ws, a.n, WS_HY, i));
+    h.inf = ld_fe(ws_at(a.ws, a.n, WS_RX, i)).v[0];
+    verify_final_check(i, a, A, B, h);
 }
 
 // ---- hash_to_curve only (rust-k256/src/utils.rs:11-20 with the preimage supplied by the caller) ----------

@@ -8,8 +8,10 @@
 //   hash_to_curve          2 lanes: the two SSWU maps (one 254-squaring exponentiation each); also plume_hash_to_curve_batch
 //   g^r, g^sk              2 lanes: one scalar each
 //   h^r, h^sk (comb)       4 lanes: (scalar, GLV half); all the doublings and half the additions each
-//   h*s - nul*c (Straus)   4 lanes: one of the four half-scalars each (all doublings, a quarter of the additions)
-//   G*s - pk*c             4 lanes: the two GLV halves of -c*pk, and the two halves of the generator windows of s
+//   h*s - nul*c            4 lanes: one of the four half-scalars each (all doublings, a quarter of the additions); the two
+//                          window tables built side by side by two of them, in the same kernel
+//   G*s - pk*c             4 lanes: the two GLV halves of -c*pk, and the two halves of the generator windows of s; on the
+//                          second stream from the start of the call
 //
 // Results are the same points in another Jacobian representation, so the outputs (affine, canonical) are bit-identical to
 // the throughput path's; tests/test_gpu_parity.py runs both on the same inputs against the oracle.  Device code only.
@@ -83,6 +85,13 @@ PLUME_DEV void sign_stage_varbase_lad_team(uint32_t mask, uint32_t idx, const si
     else ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, o);
 }
 
+// Workspace of the small-batch verifier.  h stays Jacobian from hash_to_curve to the last stage (the throughput path inverts
+// its Z right away to build the window tables from an affine h: one more inversion in the chain), so the ONE batched inversion
+// of this path has three elements per item, in three slots the throughput path uses for other things: Z of A, of B, of h.
+// Its scratch is WS_Z0 .. WS_P0, which are idle here.
+enum { TV_ZA = WS_RY, TV_ZB = WS_KX, TV_ZH = WS_KY };
+static_assert(TV_ZB == TV_ZA + 1 && TV_ZH == TV_ZA + 2, "contiguous Z slots");
+
 PLUME_DEV void verify_stage_h2c_team(uint32_t mask, uint32_t idx, const verify_args& a) {   // 2 lanes
     const uint32_t i = idx >> 1, j = idx & 1;
     uint8_t pk33[33];
@@ -92,7 +101,7 @@ PLUME_DEV void verify_stage_h2c_team(uint32_t mask, uint32_t idx, const verify_a
     uint32_t len;
     const uint8_t* m = msg_ptr(a.msgs, i, len);
     jac h = h2c_hash_to_curve_team(mask, j, m, len, pk33, npk);
-    if (j == 0) ws_store_jac(a.ws, a.n, WS_HX, WS_HY, WS_Z1, i, h);
+    if (j == 0) ws_store_jac(a.ws, a.n, WS_HX, WS_HY, TV_ZH, i, h);
 }
 
 // hash_to_curve alone (h2c_stage_map), 2 lanes
@@ -112,34 +121,64 @@ PLUME_DEV void h2c_stage_map_team(uint32_t mask, uint32_t idx, const h2c_args& a
     if (j == 0) ws_store_jac(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i, h);
 }
 
-// B = s*h - c*nul from the tables of verify_stage_mul_b1: lane q = 2 * (0: s on h, 1: -c on nul) + (GLV half)
-PLUME_DEV void verify_stage_mul_b2_team(uint32_t mask, uint32_t idx, const verify_args& a, const uint32_t* vbtab) {
+// B = s*h - c*nul, table stage and ladder stage (verify_stage_mul_b1 / _b2) in one: lane q = 2 * (0: s on h, 1: -c on nul) +
+// (GLV half).  Lanes 0 and 2 build the window table of their base side by side, each over its own denominator (no rescaling
+// of one table onto the other's curve, which the one-accumulator Straus ladder needs); every lane then walks one half-scalar,
+// the two halves of a base are added on that base's isomorphic curve, brought back with its Zg, and the two bases added.
+// h comes as the Jacobian (X, Y, Z) of hash_to_curve: (X, Y) is an affine point of the isomorphic curve with denominator Z,
+// the a = 0 formulas do not see the difference, and Z joins Zg at the end.
+// An identity among h, nul (adversarial inputs only) contributes the identity.
+PLUME_DEV void verify_stage_mul_b_team(uint32_t mask, uint32_t idx, const verify_args& a, uint32_t* vbtab) {
     const uint32_t i = idx >> 2, q = idx & 3;
-    const bool todo = ld_fe(ws_at(a.ws, a.n, WS_RY, i)).v[0] != 0;
-    mask = __ballot_sync(mask, todo);
-    if (!todo) return;   // finished in b1 (the whole team leaves)
+    const bool good = a.ok[i] != 0;
+    aff P;
+    fe zscale = fe_one();
     sc k = sc_one();
-    if (a.ok[i] != 0) {
+    if (q < 2) {
+        P.x = ld_fe(ws_at(a.ws, a.n, WS_HX, i));
+        P.y = ld_fe(ws_at(a.ws, a.n, WS_HY, i));
+        zscale = ld_fe(ws_at(a.ws, a.n, TV_ZH, i));
+        P.inf = fe_is_zero(zscale);
+    } else if (good) {
+        ld_point_be(P, a.nullifier + (size_t)i * 64);
+    } else {
+        P = aff_generator();
+    }
+    if (good) {
         k = ld_sc_be((q < 2 ? a.s : a.c) + (size_t)i * 32);
         if (q >= 2) k = sc_neg(k);
     }
-    glv_half h1, h2;
-    glv_split(k, h1, h2);
-    const uint32_t* tab = vbtab + (size_t)i * VB_ITEM_WORDS + (q < 2 ? 0 : VB_TAB_WORDS);
-    jac B = vb_ladder_half((q & 1) ? h2 : h1, (q & 1) != 0, tab);
-    B = jac_team_sum(mask, B, q, 2);
+    uint32_t* tab = vbtab + (size_t)i * VB_ITEM_WORDS + (q < 2 ? 0 : VB_TAB_WORDS);
+    fe zg = fe_one();
+    if ((q & 1) == 0 && !P.inf) {
+        zg = vb_build_table(P.x, P.y, tab, true);
+        if (q == 0) zg = fe_mul(zg, zscale);
+    }
+    __syncwarp(mask);   // the odd lane reads the table its neighbour wrote
+    jac B = jac_infinity();
+    if (!P.inf) {
+        glv_half h1, h2;
+        glv_split(k, h1, h2);
+        B = vb_ladder_half((q & 1) ? h2 : h1, (q & 1) != 0, tab);
+    }
+    B = jac_team_sum(mask, B, q & 1, 1);
+    if ((q & 1) == 0 && !B.inf) B.z = fe_mul(B.z, zg);   // (the odd lane's copy of the pair's sum is not used)
+    jac o = jac_shfl_xor(mask, B, 2);
     if (q != 0) return;
-    if (!B.inf) B.z = fe_mul(B.z, ld_fe(ws_at(a.ws, a.n, WS_KX, i)));
-    ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, B);
+    ws_store_jac(a.ws, a.n, WS_BX, WS_BY, TV_ZB, i, jac_add(B, o));
 }
 
 // A = s*G - c*pk: lanes 0, 1 the GLV halves of -c on pk's window table (lane 0 builds it), lanes 2, 3 the lower and upper
-// generator windows of s
+// generator windows of s.  Needs nothing from the other stages (it repeats the input checks instead of reading ok[]), so it
+// runs on the second stream from the start of the call.
 PLUME_DEV void verify_stage_mul_a_team(uint32_t mask, uint32_t idx, const verify_args& a, uint32_t* tab) {
     const uint32_t i = idx >> 2, q = idx & 3;
+    uint8_t pk33[33];
+    bool good;
+    verify_h2c_check(i, a, pk33, good);
     aff pk;
     sc c = sc_one(), s = sc_one();
-    if (a.ok[i] != 0) {
+    if (good) {
         ld_point_be(pk, a.pk + (size_t)i * 64);
         c = ld_sc_be(a.c + (size_t)i * 32);
         s = ld_sc_be(a.s + (size_t)i * 32);
@@ -166,5 +205,14 @@ PLUME_DEV void verify_stage_mul_a_team(uint32_t mask, uint32_t idx, const verify
     jac o = jac_shfl_xor(mask, A, 2);
     if (q != 0) return;
     A = jac_add(o, A);    // fixed-base part first, as verify_stage_mul_a does
-    ws_store_jac(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i, A);
+    ws_store_jac(a.ws, a.n, WS_AX, WS_AY, TV_ZA, i, A);
+}
+
+// last stage: one lane per item; A, B and h become affine here (TV_Z* hold the inverses)
+PLUME_DEV void verify_stage_final_team(uint32_t i, const verify_args& a) {
+    if (a.ok[i] == 0) return;
+    aff A = ws_load_affine(a.ws, a.n, WS_AX, WS_AY, TV_ZA, i);
+    aff B = ws_load_affine(a.ws, a.n, WS_BX, WS_BY, TV_ZB, i);
+    aff h = ws_load_affine(a.ws, a.n, WS_HX, WS_HY, TV_ZH, i);
+    verify_final_check(i, a, A, B, h);
 }
