@@ -101,17 +101,27 @@ int binv(plume_ctx* ctx, uint32_t* ws, uint32_t n, uint32_t m, cudaStream_t s, i
 // Small batches (n <= team_max) leave the GPU almost idle with one thread per item; what the caller waits for is the
 // length of the dependent chain, so the stages that have independent parts run them on 2 or 4 neighbouring lanes
 // (k_team.cu, stages_team.cuh).  Same workspace conventions, same results.
-int enqueue_sign(plume_ctx* ctx, sign_args a, cudaStream_t s) {
-    const bool team = a.n <= ctx->team_max;
-    RUN(ST_SIGN_FIXED, team ? launch_sign_fixed_team(a, s) : launch_sign_fixed(a, s));
+int enqueue_sign_team(plume_ctx* ctx, sign_args a, cudaStream_t s) {
+    RUN(ST_SIGN_FIXED, launch_sign_fixed_team(a, s));
     if (int rc = binv(ctx, a.ws, a.n, 2 * a.n, s)) return rc;
-    RUN(ST_SIGN_H2C, team ? launch_sign_h2c_team(a, s) : launch_sign_h2c(a, s));
+    RUN(ST_SIGN_H2C, launch_sign_h2c_team(a, s));                 // h stays Jacobian: no inversion before the table
+    RUN(ST_SIGN_TAB, launch_sign_comb_tab_small(a, s));
+    RUN(ST_SIGN_VARBASE, launch_sign_comb_lad_team(a, s));
+    if (int rc = binv(ctx, a.ws, a.n, 3 * a.n, s, WS_SLOTS, WS_SLOTS + 3)) return rc;   // TS_ZA, TS_ZB, TS_ZH; scratch TS_SCRATCH
+    RUN(ST_SIGN_FINAL, launch_sign_final_team(a, s));
+    return PLUME_OK;
+}
+int enqueue_sign(plume_ctx* ctx, sign_args a, cudaStream_t s) {
+    if (a.n <= ctx->team_max) return enqueue_sign_team(ctx, a, s);
+    RUN(ST_SIGN_FIXED, launch_sign_fixed(a, s));
+    if (int rc = binv(ctx, a.ws, a.n, 2 * a.n, s)) return rc;
+    RUN(ST_SIGN_H2C, launch_sign_h2c(a, s));
     if (int rc = binv(ctx, a.ws, a.n, a.n, s)) return rc;
 #ifdef PLUME_SIGN_ONE_KERNEL
     RUN(ST_SIGN_VARBASE, launch_sign_varbase(a, s));
 #else
-    RUN(ST_SIGN_TAB, team ? launch_sign_comb_tab_small(a, s) : launch_sign_comb_tab(a, s));
-    RUN(ST_SIGN_VARBASE, team ? launch_sign_comb_lad_team(a, s) : launch_sign_comb_lad(a, s));
+    RUN(ST_SIGN_TAB, launch_sign_comb_tab(a, s));
+    RUN(ST_SIGN_VARBASE, launch_sign_comb_lad(a, s));
 #endif
     if (int rc = binv(ctx, a.ws, a.n, 2 * a.n, s)) return rc;
     RUN(ST_SIGN_FINAL, launch_sign_final(a, s));
@@ -275,7 +285,11 @@ int lane_workspace(plume_ctx* ctx, Lane& L, size_t items) {
     if (L.ws) { cudaFree(L.ws); L.ws = nullptr; }
     if (L.vbtab) { cudaFree(L.vbtab); L.vbtab = nullptr; }
     L.ws_items = 0;
-    CU(cudaMalloc(&L.ws, (size_t)WS_SLOTS * cap * 32));
+    // The small-batch signer (<= team_max <= 4 096 items, its own n as the slot stride) uses 6 slots past WS_SLOTS
+    // (stages_team.cuh TS_*): they lie inside the allocation of any workspace for more than 5 851 items, smaller ones get the room.
+    const size_t small_items = cap < 4096 ? cap : 4096;
+    const size_t elems = std::max((size_t)WS_SLOTS * cap, (size_t)(WS_SLOTS + 6) * small_items);
+    CU(cudaMalloc(&L.ws, elems * 32));
     CU(cudaMalloc(&L.vbtab, cap * (size_t)VB_ITEM_WORDS * 4));   // comb area (sign) / two window tables (verify) per item
     L.ws_items = cap;
     return PLUME_OK;
@@ -529,6 +543,7 @@ int ctx_create_single(plume_ctx** out, int device, int fixed_window_bits, const 
     c->stage_threads = (int)env_size("PLUME_STAGE_THREADS", 8);
     c->binv_var = env_size("PLUME_BINV_VAR", 0) != 0;
     if (const char* e = getenv("PLUME_TEAM_MAX")) c->team_max = (uint32_t)strtoul(e, nullptr, 10);   // 0 switches the small-batch kernels off
+    if (c->team_max > 4096) c->team_max = 4096;   // the small-batch signer's extra workspace slots (lane_workspace)
     { const char* v = getenv("PLUME_DEVICE_SPLIT"); c->dev_split = !(v && v[0] == '0'); }
     struct Guard { plume_ctx* c; ~Guard() { if (c) plume_ctx_destroy(c); } } guard{c};
     for (int k = 0; k < 2; k++) CU(cudaStreamCreateWithFlags(&c->lanes[k].stream, cudaStreamNonBlocking));

@@ -21,6 +21,11 @@ __global__ void __launch_bounds__(128) k_verify_final_team(verify_args a) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.n) verify_stage_final_team(i, a);
 }
+__global__ void __launch_bounds__(128) k_sign_final_team(sign_args a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) sign_stage_final_team(i, a);
+}
+TEAM_LAUNCH(launch_sign_final_team, k_sign_final_team, sign_args, 1)
 TEAM_LAUNCH(launch_verify_final_team, k_verify_final_team, verify_args, 1)
 TEAM_LAUNCH(launch_h2c_map_team, k_h2c_map_team, h2c_args, 2)
 TEAM_LAUNCH(launch_sign_h2c_team, k_sign_h2c_team, sign_args, 2)

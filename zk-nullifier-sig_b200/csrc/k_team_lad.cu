@@ -1,6 +1,5 @@
 // k_team_lad.cu -- the small-batch kernels whose time is point arithmetic, compiled with the field multiplier inlined
-// (see k_team.cu).  Besides the team ladders this holds a one-lane-per-item copy of the signer's table builder (the body of
-// k_sign_comb_tab), which a small batch runs between the team kernels.
+// (see k_team.cu).  Besides the team ladders this holds the one-lane-per-item table builder of the small-batch signer.
 #define PLUME_INLINE_MUL
 // The signer's comb with 4 teeth here (5 in the throughput kernels): the chain a lone lane walks is 99 + 33 doublings, 7
 // conjugate additions for the 8 entries and 33 additions, against 104 + 26, 15 and 26 -- fewer operations in a row, more in
@@ -18,7 +17,7 @@ __global__ void __launch_bounds__(128) k_sign_fixed_team(sign_args a) {
 }
 __global__ void __launch_bounds__(128) k_sign_comb_tab_small(sign_args a) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < a.n) sign_stage_varbase_tab(i, a, a.vbtab + (size_t)i * VB_ITEM_WORDS);
+    if (i < a.n) sign_stage_varbase_tab_jac(i, a, a.vbtab + (size_t)i * VB_ITEM_WORDS);
 }
 __global__ void __launch_bounds__(128) k_sign_comb_lad_team(sign_args a) {
     TEAM_PROLOGUE(4, a.n)

@@ -50,6 +50,7 @@ cudaError_t launch_verify_h2c_team(const verify_args& a, cudaStream_t s);
 cudaError_t launch_verify_mul_b_team(const verify_args& a, cudaStream_t s);    // tables and ladders of h*s - nul*c in one
 cudaError_t launch_verify_mul_a_team(const verify_args& a, cudaStream_t s);
 cudaError_t launch_verify_final_team(const verify_args& a, cudaStream_t s);
+cudaError_t launch_sign_final_team(const sign_args& a, cudaStream_t s);
 cudaError_t launch_h2c_map(const h2c_args& a, cudaStream_t s);
 cudaError_t launch_h2c_out(const h2c_args& a, cudaStream_t s);
 cudaError_t launch_h2cw(int stage, const h2cw_args& a, cudaStream_t s);   // 0 map, 1 sum, 2 out

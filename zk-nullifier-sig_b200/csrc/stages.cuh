@@ -451,12 +451,8 @@ PLUME_DEV aff ws_load_aff_xy(uint32_t* ws, uint32_t n, int sx, int sy, uint32_t 
     return p;
 }
 
-PLUME_DEV void sign_stage_final(uint32_t i, const sign_args& a) {
-    aff z = ws_load_affine(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i);
-    aff nul = ws_load_affine(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i);
-    aff h = ws_load_aff_xy(a.ws, a.n, WS_HX, WS_HY, i);
-    aff R = ws_load_aff_xy(a.ws, a.n, WS_RX, WS_RY, i);   // the identity only in the arkworks flavour (r = 0)
-    aff K = ws_load_aff_xy(a.ws, a.n, WS_KX, WS_KY, i);
+// challenge, s = r + c sk, status and outputs from the affine points of one item (K = pk, z = h^r)
+PLUME_DEV void sign_final_finish(uint32_t i, const sign_args& a, const aff& K, const aff& h, const aff& nul, const aff& R, const aff& z) {
     uint8_t st = a.status[i];
     sc c = plume_challenge(a.version, K, h, nul, R, z);
     sc s = sc_one();
@@ -487,6 +483,14 @@ PLUME_DEV void sign_stage_final(uint32_t i, const sign_args& a) {
     else { st_zero32(a.c + (size_t)i * 32); st_zero32(a.s + (size_t)i * 32); }
     if (a.r_point) st_point_be(a.r_point + (size_t)i * 64, ok ? R : none);
     if (a.hashed_to_curve_r) st_point_be(a.hashed_to_curve_r + (size_t)i * 64, ok ? z : none);
+}
+PLUME_DEV void sign_stage_final(uint32_t i, const sign_args& a) {
+    aff z = ws_load_affine(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i);
+    aff nul = ws_load_affine(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i);
+    aff h = ws_load_aff_xy(a.ws, a.n, WS_HX, WS_HY, i);
+    aff R = ws_load_aff_xy(a.ws, a.n, WS_RX, WS_RY, i);   // the identity only in the arkworks flavour (r = 0)
+    aff K = ws_load_aff_xy(a.ws, a.n, WS_KX, WS_KY, i);
+    sign_final_finish(i, a, K, h, nul, R, z);
 }
 
 // ---- batched inversion ---------------------------------------------------------------------------------

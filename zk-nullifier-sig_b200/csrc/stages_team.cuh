@@ -47,6 +47,13 @@ PLUME_DEV void sign_stage_fixed_team(uint32_t idx, const sign_args& a) {   // 2 
     st_fe(ws_at(a.ws, a.n, j == 0 ? WS_Z0 : WS_Z1, i), P.z);
 }
 
+// Workspace of the small-batch signer.  As in the verifier below, h stays Jacobian from hash_to_curve to the last stage (the
+// throughput path inverts its Z before the comb table: one more inversion in the chain), so the last batched inversion has
+// three elements per item -- Z of h^r, of the nullifier, of h -- in three slots PAST the 14 of the throughput path, with three
+// more as its scratch: a small batch addresses the workspace with its own n as the stride, and api.cu lane_workspace sizes
+// every workspace so that slots 14..19 of a batch of <= 4 096 items lie inside it.
+enum { TS_ZA = WS_SLOTS, TS_ZB = WS_SLOTS + 1, TS_ZH = WS_SLOTS + 2, TS_SCRATCH = WS_SLOTS + 3, TS_SLOTS = WS_SLOTS + 6 };
+
 PLUME_DEV void sign_stage_h2c_team(uint32_t mask, uint32_t idx, const sign_args& a) {   // 2 lanes
     const uint32_t i = idx >> 1, j = idx & 1;
     aff R = ws_load_affine(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i);
@@ -59,11 +66,29 @@ PLUME_DEV void sign_stage_h2c_team(uint32_t mask, uint32_t idx, const sign_args&
     uint32_t npk = enc_point33(pk33, K);
     uint32_t len;
     const uint8_t* m = msg_ptr(a.msgs, i, len);
-    jac h = h2c_hash_to_curve_team(mask, j, m, len, pk33, npk);   // (both lanes have read WS_Z0 before the exchange inside)
-    if (j == 0) ws_store_jac(a.ws, a.n, WS_HX, WS_HY, WS_Z0, i, h);
+    jac h = h2c_hash_to_curve_team(mask, j, m, len, pk33, npk);
+    if (j == 0) ws_store_jac(a.ws, a.n, WS_HX, WS_HY, TS_ZH, i, h);
 }
 
-// h^r, h^sk from the comb table of sign_stage_varbase_tab: lane q = 2 * (0: r, 1: sk) + (GLV half)
+// the comb table of sign_stage_varbase_tab from the Jacobian h = (X, Y, Z): (X, Y) is an affine point of the isomorphic
+// curve with denominator Z, on which the table is built as usual; WS_P0 = the table's own denominator Zg (0: no ladders),
+// WS_P1 = Zg * Z, what the ladders' results are multiplied by.  One lane per item.
+PLUME_DEV void sign_stage_varbase_tab_jac(uint32_t i, const sign_args& a, uint32_t* area) {
+    fe hz = ld_fe(ws_at(a.ws, a.n, TS_ZH, i));
+    if (fe_is_zero(hz)) {
+        a.status[i] = PLUME_ST_H_INF;   // the reference panics here (randomizedsigner.rs:61)
+        jac o = jac_infinity();
+        ws_store_jac(a.ws, a.n, WS_AX, WS_AY, TS_ZA, i, o);
+        ws_store_jac(a.ws, a.n, WS_BX, WS_BY, TS_ZB, i, o);
+        st_fe(ws_at(a.ws, a.n, WS_P0, i), fe_zero());
+        return;
+    }
+    fe zg = comb_build_table(ld_fe(ws_at(a.ws, a.n, WS_HX, i)), ld_fe(ws_at(a.ws, a.n, WS_HY, i)), area);
+    st_fe(ws_at(a.ws, a.n, WS_P0, i), zg);
+    st_fe(ws_at(a.ws, a.n, WS_P1, i), fe_mul(zg, hz));
+}
+
+// h^r, h^sk from the comb table of sign_stage_varbase_tab_jac: lane q = 2 * (0: r, 1: sk) + (GLV half)
 PLUME_DEV void sign_stage_varbase_lad_team(uint32_t mask, uint32_t idx, const sign_args& a, const uint32_t* vbtab) {
     const uint32_t i = idx >> 2, q = idx & 3, which = q >> 1;
     fe zg = ld_fe(ws_at(a.ws, a.n, WS_P0, i));
@@ -80,9 +105,19 @@ PLUME_DEV void sign_stage_varbase_lad_team(uint32_t mask, uint32_t idx, const si
     jac o = comb_ladder_half((q & 1) ? h2 : h1, (q & 1) != 0, vbtab + (size_t)i * VB_ITEM_WORDS, hxs, hys);
     o = jac_team_sum(mask, o, q & 1, 1);
     if (q & 1) return;
-    if (!o.inf) o.z = fe_mul(o.z, zg);
-    if (which == 0) ws_store_jac(a.ws, a.n, WS_AX, WS_AY, WS_Z0, i, o);
-    else ws_store_jac(a.ws, a.n, WS_BX, WS_BY, WS_Z1, i, o);
+    if (!o.inf) o.z = fe_mul(o.z, ld_fe(ws_at(a.ws, a.n, WS_P1, i)));
+    if (which == 0) ws_store_jac(a.ws, a.n, WS_AX, WS_AY, TS_ZA, i, o);
+    else ws_store_jac(a.ws, a.n, WS_BX, WS_BY, TS_ZB, i, o);
+}
+
+// last stage: one lane per item; h^r, the nullifier and h become affine here (TS_Z* hold the inverses)
+PLUME_DEV void sign_stage_final_team(uint32_t i, const sign_args& a) {
+    aff z = ws_load_affine(a.ws, a.n, WS_AX, WS_AY, TS_ZA, i);
+    aff nul = ws_load_affine(a.ws, a.n, WS_BX, WS_BY, TS_ZB, i);
+    aff h = ws_load_affine(a.ws, a.n, WS_HX, WS_HY, TS_ZH, i);
+    aff R = ws_load_aff_xy(a.ws, a.n, WS_RX, WS_RY, i);
+    aff K = ws_load_aff_xy(a.ws, a.n, WS_KX, WS_KY, i);
+    sign_final_finish(i, a, K, h, nul, R, z);
 }
 
 // Workspace of the small-batch verifier.  h stays Jacobian from hash_to_curve to the last stage (the throughput path inverts
