@@ -245,7 +245,7 @@ def test_small_batch_latency(gpu_ctx):
     rust-k256/src/lib.rs:149-156, as the drop-in shim uses it).  A regression guard, not a target: round 1 measured
     1.6 ms to sign and 1.9 ms to verify one signature; the stage split and the second stream for G*s - pk*c brought that to
     1.15 / 1.25 ms, the small-batch kernels (k_team.cu: 2 or 4 lanes per item) and the division-step inversion (inv.cuh) to
-    0.79 / 0.72 ms on a B200 (profiles/r02_small_batch.md).  The bound leaves room for a noisy box."""
+    0.76 / 0.64 ms on a B200 (profiles/r02_small_batch.md).  The bound leaves room for a noisy box."""
     import time
     rng = np.random.default_rng(8)
     for n in (1, 1024):
