@@ -120,6 +120,9 @@ size_t plume_ctx_chunk_items(const plume_ctx* ctx);
  *   r_point            n x 64   out: g^r           (V1 field; may be NULL)
  *   hashed_to_curve_r  n x 64   out: h^r           (V1 field; may be NULL)
  *   status             n        out: PLUME_STATUS_*; on a non-zero status every output of the item is zero
+ * Any n is legal.  Batches of at most 4 096 items (environment: PLUME_TEAM_MAX) run kernels built for latency -- 2 or 4
+ * lanes of a warp per item -- with bit-identical results: one signature takes ~0.76 ms, one verification ~0.64 ms on a
+ * B200; the throughput figures need 10^5 items and more.
  */
 int plume_sign_batch(plume_ctx* ctx, int version, size_t n,
                      const uint8_t* msgs, const uint64_t* msg_offsets, size_t msg_len,
