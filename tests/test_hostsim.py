@@ -55,7 +55,10 @@ def test_division_step_inversion():
             2**224 - 1, (1 << 256) - (1 << 224), 0x5555555555555555555555555555555555555555555555555555555555555555 % 2**256,
             0xAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA]
     vals += [1 << k for k in range(0, 256, 7)] + [(1 << k) - 1 for k in range(2, 256, 11)] + [P - (1 << k) for k in range(0, 250, 13)]
-    vals += [rnd.randrange(2**256) for _ in range(1500)] + [rnd.randrange(2**64) for _ in range(50)]
+    vals += [rnd.randrange(2**256) for _ in range(20000)] + [rnd.randrange(2**64) for _ in range(200)]
+    vals += [rnd.getrandbits(256) & rnd.getrandbits(256) & rnd.getrandbits(256) for _ in range(500)]          # sparse
+    vals += [(rnd.getrandbits(256) | rnd.getrandbits(256) | rnd.getrandbits(256)) for _ in range(500)]        # dense
+    vals += [pow(a, -1, P) for a in (2, 3, 2**30, 2**60, 2**255)] + [P - pow(2, -k, P) for k in (1, 30, 31, 60)]
     for a in vals:
         got = H.fe_op(14, a) % P
         assert got == (pow(a, -1, P) if a % P else 0), hex(a)
